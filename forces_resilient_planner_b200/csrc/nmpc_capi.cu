@@ -1,0 +1,495 @@
+// nmpc_capi.cu -- C ABI of libnmpc_b200.so (see include/nmpc_b200.h).
+//
+// Host side of the drop-in: the batched entry points, and the two reference-named symbols
+//   FORCESNLPsolver_normal_solve / FORCESNLPsolver_final_solve
+// that plan_manage/src/forces_normal.cpp:139 and forces_final.cpp:138 call.  No CPU fallback
+// exists anywhere in this file: every path ends in the sm_100a kernel or in an error code.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/FORCESNLPsolver_final.h"
+#include "../../include/FORCESNLPsolver_normal.h"
+#include "../../include/nmpc_b200.h"
+#include "nmpc_backsolve.cuh"
+#include "nmpc_ipm.cuh"
+#include "nmpc_prep.cuh"
+
+// ---- the ABI contract of the reference headers --------------------------------
+static_assert(sizeof(FORCESNLPsolver_normal_params) == 23600, "params size");
+static_assert(offsetof(FORCESNLPsolver_normal_params, x0) == 72, "x0 offset");
+static_assert(offsetof(FORCESNLPsolver_normal_params, all_parameters) == 2792, "all_parameters offset");
+static_assert(offsetof(FORCESNLPsolver_normal_params, num_of_threads) == 23592, "num_of_threads offset");
+static_assert(sizeof(FORCESNLPsolver_normal_output) == 2720, "output size");
+static_assert(sizeof(FORCESNLPsolver_normal_info) == 136, "info size");
+static_assert(offsetof(FORCESNLPsolver_normal_info, res_eq) == 8, "res_eq offset");
+static_assert(offsetof(FORCESNLPsolver_normal_info, lsit_aff) == 96, "lsit_aff offset");
+static_assert(offsetof(FORCESNLPsolver_normal_info, step_aff) == 104, "step_aff offset");
+static_assert(offsetof(FORCESNLPsolver_normal_info, solvetime) == 120, "solvetime offset");
+static_assert(sizeof(FORCESNLPsolver_final_params) == 23600 && sizeof(FORCESNLPsolver_final_output) == 2720 &&
+                  sizeof(FORCESNLPsolver_final_info) == 136, "final ABI");
+static_assert(sizeof(nmpc_opts) == sizeof(nmpc::Opts), "opts mirror");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(NMPC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));     \
+    } while (0)
+
+template <typename T, int N>
+int launch(const nmpc::Params<T>& prm, cudaStream_t st)
+{
+    using L = nmpc::Layout<T, N>;
+    if (!L::staging_fits(prm.mcap)) return fail(NMPC_ERR_ARG, "mcap=%d too large for the staging area", prm.mcap);
+    const size_t smem = L::bytes(prm.mcap);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::nmpc_ipm_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    nmpc::nmpc_ipm_kernel<T, N><<<prm.B, 32, smem, st>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr, const T* rows,
+                 const int* nrows, int variant, const nmpc_opts* opts, T* z_out, int* info_int,
+                 T* info_real, void* stream, T* y_out = nullptr, T* zl_out = nullptr, T* zu_out = nullptr,
+                 T* lc_out = nullptr)
+{
+    if (B < 0 || mcap < 0 || mcap > 32 || (variant != 0 && variant != 1))
+        return fail(NMPC_ERR_ARG, "bad argument: B=%d mcap=%d variant=%d", B, mcap, variant);
+    if (!nmpc_supported_horizon(N)) return fail(NMPC_ERR_ARG, "unsupported horizon N=%d (20 or 40)", N);
+    if (B == 0) return 0;
+    if (!xinit || !z0 || !hdr || !nrows || !z_out || !info_int || !info_real || (mcap > 0 && !rows))
+        return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::Params<T> prm;
+    prm.B = B; prm.mcap = mcap; prm.variant = variant;
+    prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows;
+    prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
+    prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
+    nmpc_opts o;
+    if (opts) o = *opts; else nmpc_default_opts(&o);
+    if (!(o.mu0 > 0) || !(o.mu_floor > 0) || o.maxit < 0 || o.max_bt < 0)
+        return fail(NMPC_ERR_ARG, "bad solver options");
+    std::memcpy(&prm.o, &o, sizeof(o));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return N == 20 ? launch<T, 20>(prm, st) : launch<T, 40>(prm, st);
+}
+
+template <typename T, int N>
+int launch_factor(const nmpc::FactorParams<T>& q, cudaStream_t st)
+{
+    const size_t smem = nmpc::Layout<T, N>::bytes(0);
+    static thread_local bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::riccati_factor_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    nmpc::riccati_factor_kernel<T, N><<<q.B, 32, smem, st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <typename T, int N>
+int launch_backsolve(const nmpc::BacksolveParams<T>& q, cudaStream_t st)
+{
+    const size_t smem = nmpc::BsLayout<T, N>::bytes();
+    static thread_local bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::kkt_backsolve_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    nmpc::kkt_backsolve_kernel<T, N><<<q.B, 32, smem, st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <typename T>
+int factor_device(int B, int N, const T* phi, const T* jc, T* fac, int* status, void* stream)
+{
+    if (B < 0 || !nmpc_supported_horizon(N)) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
+    if (B == 0) return 0;
+    if (!phi || !jc || !fac || !status) return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::FactorParams<T> q{B, phi, jc, fac, status};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return N == 20 ? launch_factor<T, 20>(q, st) : launch_factor<T, 40>(q, st);
+}
+template <typename T>
+int backsolve_device(int B, int N, const T* fac, const T* g, const T* d, T* dz, T* y, void* stream)
+{
+    if (B < 0 || !nmpc_supported_horizon(N)) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
+    if (B == 0) return 0;
+    if (!fac || !g || !d || !dz || !y) return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::BacksolveParams<T> q{B, fac, g, d, dz, y};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return N == 20 ? launch_backsolve<T, 20>(q, st) : launch_backsolve<T, 40>(q, st);
+}
+
+// grow-only device arena for the host-pointer API and the FORCES shim
+struct Arena {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CUDA_TRY(cudaMalloc(&p, n));
+        cap = n;
+        return 0;
+    }
+};
+std::mutex g_host_mutex;   // the reference solver is non-reentrant (static workspace); mirror that
+Arena g_arena;
+cudaStream_t g_stream = nullptr;
+
+inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+template <typename T>
+int solve_host(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr, const T* rows,
+               const int* nrows, int variant, const nmpc_opts* opts, T* z_out, int* info_int, T* info_real)
+{
+    if (B < 0) return fail(NMPC_ERR_ARG, "B < 0");
+    if (B == 0) return 0;
+    if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return fail(NMPC_ERR_ARG, "bad N=%d or mcap=%d", N, mcap);
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    const size_t n_x = (size_t)B * 9 * sizeof(T), n_z = (size_t)B * N * 17 * sizeof(T);
+    const size_t n_h = (size_t)B * N * 10 * sizeof(T), n_r = (size_t)B * N * mcap * 4 * sizeof(T);
+    const size_t n_n = (size_t)B * N * sizeof(int), n_ii = (size_t)B * 4 * sizeof(int), n_ir = (size_t)B * 8 * sizeof(T);
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += align256(n ? n : 1); return o; };
+    const size_t o_x = take(n_x), o_z = take(n_z), o_h = take(n_h), o_r = take(n_r), o_n = take(n_n);
+    const size_t o_zo = take(n_z), o_ii = take(n_ii), o_ir = take(n_ir);
+    if (int rc = g_arena.reserve(off)) return rc;
+    char* base = static_cast<char*>(g_arena.p);
+    CUDA_TRY(cudaMemcpyAsync(base + o_x, xinit, n_x, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_z, z0, n_z, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_h, hdr, n_h, cudaMemcpyHostToDevice, g_stream));
+    if (n_r) CUDA_TRY(cudaMemcpyAsync(base + o_r, rows, n_r, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_n, nrows, n_n, cudaMemcpyHostToDevice, g_stream));
+    int rc = solve_device<T>(B, N, mcap, (const T*)(base + o_x), (const T*)(base + o_z), (const T*)(base + o_h),
+                             (const T*)(base + o_r), (const int*)(base + o_n), variant, opts,
+                             (T*)(base + o_zo), (int*)(base + o_ii), (T*)(base + o_ir), g_stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(z_out, base + o_zo, n_z, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(info_int, base + o_ii, n_ii, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(info_real, base + o_ir, n_ir, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// ---- reference ABI shim ------------------------------------------------------------------------
+// Unpacks the 130-slot per-stage parameter layout (matlab_code/setup.m:60-66) into the native one.
+// All-zero padding rows (forces_normal.cpp:127-135: A = 0, b = 0, i.e. the constant 0 <= 1e-5)
+// carry no information and are dropped.
+int forces_solve(const double* xinit, const double* x0, const double* allp, double* out340,
+                 int variant, int* it, int* nbt, double ir[8], double* seconds)
+{
+    constexpr int N = 20;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<double> hdr(N * 10);
+    std::vector<int> nrows(N, 0);
+    int mcap = 1;
+    for (int k = 0; k < N; k++) {
+        const double* p = allp + k * 130;
+        int m = 0;
+        for (int j = 0; j < 30; j++)
+            if (p[10 + 3 * j] != 0.0 || p[11 + 3 * j] != 0.0 || p[12 + 3 * j] != 0.0 || p[100 + j] != 0.0) m++;
+        nrows[k] = m;
+        if (m > mcap) mcap = m;
+    }
+    std::vector<double> rows((size_t)N * mcap * 4, 0.0);
+    for (int k = 0; k < N; k++) {
+        const double* p = allp + k * 130;
+        std::memcpy(&hdr[k * 10], p, 10 * sizeof(double));
+        int m = 0;
+        for (int j = 0; j < 30; j++) {
+            if (p[10 + 3 * j] == 0.0 && p[11 + 3 * j] == 0.0 && p[12 + 3 * j] == 0.0 && p[100 + j] == 0.0) continue;
+            double* r = &rows[((size_t)k * mcap + m) * 4];
+            r[0] = p[10 + 3 * j]; r[1] = p[11 + 3 * j]; r[2] = p[12 + 3 * j]; r[3] = p[100 + j];
+            m++;
+        }
+    }
+    int ii[4] = {0, 0, 0, 0};
+    int rc = solve_host<double>(1, N, mcap, xinit, x0, hdr.data(), rows.data(), nrows.data(), variant, nullptr,
+                                out340, ii, ir);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) return rc == NMPC_ERR_ARG ? -11 : rc;
+    *it = ii[1]; *nbt = ii[2];
+    return ii[0];
+}
+
+template <typename Info>
+void fill_info(Info* info, int it, int nbt, const double ir[8], double seconds)
+{
+    if (!info) return;
+    const double n_ineq = 2 * (8 + 19 * 17);   // bound pairs; corridor rows vary, reported via mu
+    info->it = it; info->it2opt = it;
+    info->res_eq = ir[0]; info->res_ineq = ir[1]; info->rsnorm = ir[2]; info->rcompnorm = ir[3];
+    info->pobj = ir[4];
+    info->dgap = ir[5] * n_ineq;
+    info->dobj = ir[4] - info->dgap;
+    info->rdgap = ir[4] != 0.0 ? std::fabs(info->dgap / ir[4]) : 0.0;
+    info->mu = ir[5]; info->mu_aff = ir[5]; info->sigma = 0.1;
+    info->lsit_aff = 0; info->lsit_cc = nbt;
+    info->step_aff = ir[7]; info->step_cc = ir[6];
+    info->solvetime = seconds; info->fevalstime = 0.0;
+}
+
+// ---- device model probe (tests): evaluates the device model exactly as the solver does -----------
+__global__ void model_eval_kernel(int n, const double* z, const double* p, const int* stage, int n_stages,
+                                  int variant, double* f, double* grad, double* c, double* jc, double* h, double* jh)
+{
+    using namespace nmpc;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double* zt = z + (size_t)t * 17;
+    const double* pt = p + (size_t)t * 130;
+    const int st = stage[t];
+    double zk[NZ], g[NZ], cc[NXI], jcomp[NJC];
+    for (int i = 0; i < NZ; i++) zk[i] = zt[i];
+    f[t] = objective<double, true>(zk, pt, st == 0, variant == 1 && st == n_stages - 1, g);
+    for (int i = 0; i < NZ; i++) grad[(size_t)t * 17 + i] = g[i];
+    dynamics<double, true>(zk, pt + 3, cc, jcomp);
+    for (int i = 0; i < NXI; i++) c[(size_t)t * 13 + i] = cc[i];
+    // expand the compact Jacobian through the very accessor the solver uses (jt_y on unit vectors)
+    for (int r = 0; r < NXI; r++) {
+        double e[NXI];
+        for (int i = 0; i < NXI; i++) e[i] = (i == r) ? 1.0 : 0.0;
+        for (int col = 0; col < NZ; col++) jc[(size_t)t * 221 + col * 13 + r] = jt_y<double>(jcomp, e, col);
+    }
+    for (int j = 0; j < 30; j++) {
+        const double a0 = pt[10 + 3 * j], a1 = pt[11 + 3 * j], a2 = pt[12 + 3 * j];
+        h[(size_t)t * 30 + j] = a0 * zk[8] + a1 * zk[9] + a2 * zk[10] - pt[100 + j];
+        for (int col = 0; col < NZ; col++)
+            jh[(size_t)t * 510 + col * 30 + j] = col == 8 ? a0 : (col == 9 ? a1 : (col == 10 ? a2 : 0.0));
+    }
+}
+
+// ---- FMA-issue probe: the roofline denominator MEASURED_PEAKS.json does not carry (fp64 / fp32 CUDA cores)
+template <typename T> __global__ void fma_probe_kernel(int iters, T* sink)
+{
+    T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+    const T m = T(0.999999), c = T(1e-6);
+    for (int i = 0; i < iters; i++) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == T(-1)) sink[0] = a0;
+}
+template <typename T> int fma_probe(double* tflops)
+{
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T* sink;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(T)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 16, blocks = sms * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        fma_probe_kernel<T><<<blocks, threads>>>(iters, sink);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = best;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nmpc_fma_peak_probe(int elem_size, double* tflops)
+{
+    if (!tflops || (elem_size != 8 && elem_size != 4)) return fail(NMPC_ERR_ARG, "bad argument");
+    return elem_size == 8 ? fma_probe<double>(tflops) : fma_probe<float>(tflops);
+}
+
+void nmpc_default_opts(nmpc_opts* o)
+{
+    o->mu0 = 1.0; o->sigma = 0.1; o->mu_floor = 1e-5;
+    o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-4;
+    o->kappa_push = 1e-2; o->s_floor = 1e-2;
+    o->maxit = 200; o->max_bt = 6;
+}
+
+const char* nmpc_last_error(void) { return g_err; }
+const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a; fused warp-per-problem IPM)"; }
+int nmpc_supported_horizon(int N) { return N == 20 || N == 40; }
+
+long nmpc_smem_bytes(int N, int mcap, int elem_size)
+{
+    if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return -1;
+    if (elem_size == 8) return N == 20 ? (long)nmpc::Layout<double, 20>::bytes(mcap) : (long)nmpc::Layout<double, 40>::bytes(mcap);
+    if (elem_size == 4) return N == 20 ? (long)nmpc::Layout<float, 20>::bytes(mcap) : (long)nmpc::Layout<float, 40>::bytes(mcap);
+    return -1;
+}
+
+int nmpc_solve_batch_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                         const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
+                         int* info_int, double* info_real, void* cuda_stream)
+{
+    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream);
+}
+int nmpc_solve_batch_f32(int B, int N, int mcap, const float* xinit, const float* z0, const float* hdr,
+                         const float* rows, const int* nrows, int variant, const nmpc_opts* opts, float* z_out,
+                         int* info_int, float* info_real, void* cuda_stream)
+{
+    return solve_device<float>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream);
+}
+int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                            const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
+                            int* info_int, double* info_real, double* y_out, double* zl_out, double* zu_out,
+                            double* lc_out, void* cuda_stream)
+{
+    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
+                                cuda_stream, y_out, zl_out, zu_out, lc_out);
+}
+int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                              const double* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                              double* z_out, int* info_int, double* info_real)
+{
+    return solve_host<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real);
+}
+int nmpc_solve_batch_host_f32(int B, int N, int mcap, const float* xinit, const float* z0, const float* hdr,
+                              const float* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                              float* z_out, int* info_int, float* info_real)
+{
+    return solve_host<float>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real);
+}
+
+int nmpc_backsolve_factor_words(void) { return nmpc::FAC_WORDS; }
+long nmpc_backsolve_algorithmic_bytes(int N, int elem_size) { return (long)N * (nmpc::FAC_WORDS + 2 * (17 + 13)) * elem_size; }
+
+int nmpc_riccati_factor_f64(int B, int N, const double* phi, const double* jc, double* fac, int* status, void* stream)
+{
+    return factor_device<double>(B, N, phi, jc, fac, status, stream);
+}
+int nmpc_riccati_factor_f32(int B, int N, const float* phi, const float* jc, float* fac, int* status, void* stream)
+{
+    return factor_device<float>(B, N, phi, jc, fac, status, stream);
+}
+int nmpc_kkt_backsolve_f64(int B, int N, const double* fac, const double* g, const double* d, double* dz, double* y, void* stream)
+{
+    return backsolve_device<double>(B, N, fac, g, d, dz, y, stream);
+}
+int nmpc_kkt_backsolve_f32(int B, int N, const float* fac, const float* g, const float* d, float* dz, float* y, void* stream)
+{
+    return backsolve_device<float>(B, N, fac, g, d, dz, y, stream);
+}
+
+int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double* ref_pos, const double* ref_yaw,
+                         const double* ext_acc, const double* ellipsoid, const double* poly_A, const double* poly_b,
+                         const int* poly_m, const int* poly_idx, const double* weights5, double* hdr, double* rows,
+                         int* nrows, void* stream)
+{
+    if (B < 0 || N <= 0 || P <= 0 || M <= 0 || mcap <= 0 || mcap > 32) return fail(NMPC_ERR_ARG, "bad argument");
+    if (B == 0) return 0;
+    if (!ref_pos || !ref_yaw || !ext_acc || !ellipsoid || !poly_A || !poly_b || !poly_m || !poly_idx || !weights5 || !hdr || !rows || !nrows)
+        return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::PackParams q{B, N, P, M, mcap, ref_pos, ref_yaw, ext_acc, ellipsoid, poly_A, poly_b, poly_m, poly_idx,
+                       weights5[0], weights5[1], weights5[2], weights5[3], weights5[4], hdr, rows, nrows};
+    const int n = B * N;
+    nmpc::pack_params_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nmpc_shift_warm_start_f64(int B, int N, const double* z_prev, double* xinit, double* z0, int wrap_yaw, void* stream)
+{
+    if (B < 0 || N <= 1) return fail(NMPC_ERR_ARG, "bad argument");
+    if (B == 0) return 0;
+    if (!z_prev || !xinit || !z0) return fail(NMPC_ERR_ARG, "null pointer argument");
+    const int n = B * N;
+    nmpc::shift_warm_start_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(B, N, z_prev, xinit, z0, wrap_yaw);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nmpc_model_eval_host_f64(int n, const double* z, const double* p, const int* stage, int n_stages, int variant,
+                             double* f, double* grad, double* c, double* jc, double* h, double* jh)
+{
+    if (n <= 0) return 0;
+    double *dz, *dp, *df, *dg, *dc, *djc, *dh, *djh;
+    int* ds;
+    CUDA_TRY(cudaMalloc(&dz, (size_t)n * 17 * 8)); CUDA_TRY(cudaMalloc(&dp, (size_t)n * 130 * 8));
+    CUDA_TRY(cudaMalloc(&ds, (size_t)n * 4)); CUDA_TRY(cudaMalloc(&df, (size_t)n * 8));
+    CUDA_TRY(cudaMalloc(&dg, (size_t)n * 17 * 8)); CUDA_TRY(cudaMalloc(&dc, (size_t)n * 13 * 8));
+    CUDA_TRY(cudaMalloc(&djc, (size_t)n * 221 * 8)); CUDA_TRY(cudaMalloc(&dh, (size_t)n * 30 * 8));
+    CUDA_TRY(cudaMalloc(&djh, (size_t)n * 510 * 8));
+    CUDA_TRY(cudaMemcpy(dz, z, (size_t)n * 17 * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dp, p, (size_t)n * 130 * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ds, stage, (size_t)n * 4, cudaMemcpyHostToDevice));
+    model_eval_kernel<<<(n + 63) / 64, 64>>>(n, dz, dp, ds, n_stages, variant, df, dg, dc, djc, dh, djh);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(f, df, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(grad, dg, (size_t)n * 17 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(c, dc, (size_t)n * 13 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(jc, djc, (size_t)n * 221 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h, dh, (size_t)n * 30 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(jh, djh, (size_t)n * 510 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dz); cudaFree(dp); cudaFree(ds); cudaFree(df); cudaFree(dg); cudaFree(dc); cudaFree(djc); cudaFree(dh); cudaFree(djh);
+    return 0;
+}
+
+// ---- the reference's solver symbols ---------------------------------------------------------------
+solver_int32_default FORCESNLPsolver_normal_solve(FORCESNLPsolver_normal_params* params,
+                                                  FORCESNLPsolver_normal_output* output,
+                                                  FORCESNLPsolver_normal_info* info, FILE* fs,
+                                                  FORCESNLPsolver_normal_extfunc /*ignored: device model built in*/)
+{
+    if (!params || !output) return PARAM_VALUE_ERROR_FORCESNLPsolver_normal;
+    int it = 0, nbt = 0; double ir[8] = {0}, sec = 0;
+    int flag = forces_solve(params->xinit, params->x0, params->all_parameters, output->x01, 0, &it, &nbt, ir, &sec);
+    fill_info(info, it, nbt, ir, sec);
+    if (fs) fprintf(fs, "FORCESNLPsolver_normal (nmpc_b200): exitflag %d, it %d, pobj %.6e, res_eq %.2e, rsnorm %.2e, time %.3e s%s%s\n",
+                    flag, it, ir[4], ir[0], ir[2], sec, flag <= -100 ? " -- " : "", flag <= -100 ? g_err : "");
+    return flag;
+}
+
+solver_int32_default FORCESNLPsolver_final_solve(FORCESNLPsolver_final_params* params,
+                                                 FORCESNLPsolver_final_output* output,
+                                                 FORCESNLPsolver_final_info* info, FILE* fs,
+                                                 FORCESNLPsolver_final_extfunc /*ignored*/)
+{
+    if (!params || !output) return PARAM_VALUE_ERROR_FORCESNLPsolver_final;
+    int it = 0, nbt = 0; double ir[8] = {0}, sec = 0;
+    int flag = forces_solve(params->xinit, params->x0, params->all_parameters, output->x01, 1, &it, &nbt, ir, &sec);
+    fill_info(info, it, nbt, ir, sec);
+    if (fs) fprintf(fs, "FORCESNLPsolver_final (nmpc_b200): exitflag %d, it %d, pobj %.6e, res_eq %.2e, rsnorm %.2e, time %.3e s%s%s\n",
+                    flag, it, ir[4], ir[0], ir[2], sec, flag <= -100 ? " -- " : "", flag <= -100 ? g_err : "");
+    return flag;
+}
+
+}  // extern "C"

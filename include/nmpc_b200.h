@@ -1,0 +1,147 @@
+/*
+ * nmpc_b200.h -- C ABI of the B200-native batched NMPC solver (libnmpc_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in any signature (streams travel as void*).
+ *
+ * Two families of entry points:
+ *
+ *  (1) the reference's own solver ABI, preserved bit for bit, so that
+ *      plan_manage/src/forces_normal.cpp:139 and forces_final.cpp:138 link unchanged:
+ *          FORCESNLPsolver_normal_solve / FORCESNLPsolver_final_solve
+ *      -> declared in include/FORCESNLPsolver_normal.h and include/FORCESNLPsolver_final.h.
+ *
+ *  (2) the batched entry points this file declares.  They take the same information as
+ *      FORCESNLPsolver_normal_params (reference:
+ *      solver/normal/FORCESNLPsolver_normal/include/FORCESNLPsolver_normal.h:153-168) for B
+ *      independent problems, in a layout without the 30-row zero padding:
+ *
+ *        xinit [B][9]           <- params.xinit                     (header :156)
+ *        z0    [B][N][17]       <- params.x0                        (header :159)
+ *        hdr   [B][N][10]       <- params.all_parameters[k*130+0..9]   ref(3) f_ext(3) w_wp w_in w_rate yaw_ref
+ *        rows  [B][N][mcap][4]  <- all_parameters[k*130+10+3j..] and [k*130+100+j]   (a0 a1 a2 b), a.pos <= b
+ *        nrows [B][N] int32     <- number of live rows of each stage (<= mcap)
+ *        z_out [B][N][17]       -> output.x01 .. x20                (header :173-236)
+ *        info_int  [B][4]       -> exitflag (reference codes, header :110-139), iterations, backtracks, 0
+ *        info_real [B][8]       -> res_eq, res_ineq, rsnorm, rcompnorm, pobj, mu, alpha_p, alpha_d
+ *                                  (the fields of FORCESNLPsolver_normal_info, header :241-301)
+ *
+ *      variant 0 = "normal" stage/terminal costs, 1 = "final" (terminal velocity cost,
+ *      matlab_code/mpc/final/mpc_objectiveN_final.m:26).
+ *
+ * Return value of every nmpc_* function: 0 on success, <0 on failure
+ * (NMPC_ERR_*; nmpc_last_error() gives the text).  Per-problem solver outcomes are in info_int.
+ * There is NO CPU fallback: without a CUDA device every solve entry point returns NMPC_ERR_CUDA.
+ */
+#ifndef NMPC_B200_H
+#define NMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMPC_ERR_ARG (-11)    /* invalid argument (mirrors PARAM_VALUE_ERROR, header :131) */
+#define NMPC_ERR_CUDA (-101)  /* CUDA runtime failure / no device                           */
+
+typedef struct nmpc_opts {
+    double mu0;        /* initial barrier parameter                          (default 1.0)   */
+    double sigma;      /* centering; <= 0 selects the LOQO centrality rule   (default 0.1)   */
+    double mu_floor;   /* lowest barrier target                              (default 1e-5)  */
+    double tol_stat;   /* codeoptions.nlp.TolStat  (mpc_generator_normal.m:76)  1e-4         */
+    double tol_eq;     /* codeoptions.nlp.TolEq    (:77)                         1e-4         */
+    double tol_ineq;   /* codeoptions.nlp.TolIneq  (:78)                         1e-4         */
+    double tol_comp;   /* codeoptions.nlp.TolComp  (:79)                         1e-4         */
+    double kappa_push; /* push of the initial guess into the bound interior  (default 1e-2)  */
+    double s_floor;    /* floor on initial corridor slacks                   (default 1e-2)  */
+    int maxit;         /* codeoptions.maxit (:56)                            200             */
+    int max_bt;        /* backtracking steps per iteration                   (default 6)     */
+} nmpc_opts;
+
+void nmpc_default_opts(nmpc_opts *o);
+const char *nmpc_last_error(void);
+const char *nmpc_version(void);
+
+/* Supported horizons N: 20 (the reference), 40 (BASELINE config 4).  mcap in [0, 32]. */
+int nmpc_supported_horizon(int N);
+/* dynamic shared memory one problem occupies (bytes); elem_size 8 (f64) or 4 (f32) */
+long nmpc_smem_bytes(int N, int mcap, int elem_size);
+
+/* ---- device-pointer API: everything already resident in HBM, asynchronous on `stream` -------- */
+int nmpc_solve_batch_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                         const double *hdr, const double *rows, const int *nrows, int variant,
+                         const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,
+                         void *cuda_stream);
+int nmpc_solve_batch_f32(int B, int N, int mcap, const float *xinit, const float *z0,
+                         const float *hdr, const float *rows, const int *nrows, int variant,
+                         const nmpc_opts *opts, float *z_out, int *info_int, float *info_real,
+                         void *cuda_stream);
+
+/* as nmpc_solve_batch_f64, additionally returning the multipliers of the KKT point (any of the
+ * four may be NULL): y_out [B][N][13] (c-ordering [x+(9); u(4)], y[0] = 0), zl_out / zu_out
+ * [B][N][17], lc_out [B][N][mcap].  Used to check ForcesPro's acceptance test with the
+ * reference callbacks (stationarity needs the multipliers).                                    */
+int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                            const double *hdr, const double *rows, const int *nrows, int variant,
+                            const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,
+                            double *y_out, double *zl_out, double *zu_out, double *lc_out,
+                            void *cuda_stream);
+
+/* ---- host-pointer API: H2D copies, solve, D2H copies, synchronous --------------------------- */
+int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                              const double *hdr, const double *rows, const int *nrows, int variant,
+                              const nmpc_opts *opts, double *z_out, int *info_int, double *info_real);
+int nmpc_solve_batch_host_f32(int B, int N, int mcap, const float *xinit, const float *z0,
+                              const float *hdr, const float *rows, const int *nrows, int variant,
+                              const nmpc_opts *opts, float *z_out, int *info_int, float *info_real);
+
+/* ---- stand-alone structured KKT factorisation / backsolve (device pointers) ------------------
+ * The split the reference binary makes internally (f_17_PD_ldlchol_rowmajor ... vs
+ * f_17_ldl_forward_solve_rm / f_13_backward_solve_rm) for the Riccati factor:
+ *   phi [B][N][21]  stage Hessian, compact: diag(17) | pos block off-diag (01,02,12) | H[u_i][uprev_i]
+ *   jc  [B][N][51]  compact dynamics Jacobian (pos+/vel+ wrt vel, rpy, thrust; vel+ wrt rates)
+ *   fac [B][N][nmpc_backsolve_factor_words()]   P_k packed 91 | K_k 52 | Quu^-1 packed 10 | J_k 51
+ *   g   [B][N][17], d [B][N][13] (c-ordering, row N-1 unused)  ->  dz [B][N][17], y [B][N][13]
+ * solving   min 1/2 dz'Phi dz + g'dz  s.t.  E dz_{k+1} = J_k dz_k + d_k,  dz_0[8:17] = 0.         */
+int nmpc_backsolve_factor_words(void);
+long nmpc_backsolve_algorithmic_bytes(int N, int elem_size);
+int nmpc_riccati_factor_f64(int B, int N, const double *phi, const double *jc, double *fac,
+                            int *status, void *cuda_stream);
+int nmpc_riccati_factor_f32(int B, int N, const float *phi, const float *jc, float *fac,
+                            int *status, void *cuda_stream);
+int nmpc_kkt_backsolve_f64(int B, int N, const double *fac, const double *g, const double *d,
+                           double *dz, double *y, void *cuda_stream);
+int nmpc_kkt_backsolve_f32(int B, int N, const float *fac, const float *g, const float *d,
+                           float *dz, float *y, void *cuda_stream);
+
+/* ---- the steps around the solve, device-resident ----------------------
+ * nmpc_pack_params_f64: batched body of FORCESNormal::solveNormal (forces_normal.cpp:100-136):
+ *   ref_pos [B][N][3], ref_yaw [B][N], ext_acc [B][3], ellipsoid [B][N][9] (E_i row-major),
+ *   poly_A [B][P][M][3], poly_b [B][P][M], poly_m [B][P], poly_idx [B][N],
+ *   weights5 (HOST) = w_stage_wp, w_stage_input, w_input_rate, w_terminal_wp, w_terminal_input
+ *   -> hdr [B][N][10], rows [B][N][mcap][4] with b_j - ||E_i a_j||, nrows [B][N] (truncated at mcap)
+ * nmpc_shift_warm_start_f64: z_prev [B][N][17] -> z0 (shifted, last stage duplicated), xinit [B][9]
+ *   (forces_normal.cpp:62-97, nmpc_solver.cpp:531-543); wrap_yaw != 0 wraps yaw into (-pi, pi].   */
+int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double *ref_pos,
+                         const double *ref_yaw, const double *ext_acc, const double *ellipsoid,
+                         const double *poly_A, const double *poly_b, const int *poly_m,
+                         const int *poly_idx, const double *weights5, double *hdr, double *rows,
+                         int *nrows, void *cuda_stream);
+int nmpc_shift_warm_start_f64(int B, int N, const double *z_prev, double *xinit, double *z0,
+                              int wrap_yaw, void *cuda_stream);
+
+/* ---- measured CUDA-core FMA peak (TFLOP/s) of the current device, elem_size 8 (fp64) or 4 (fp32):
+ * the roofline denominator for the fused solver kernel, which is FMA-issue/latency bound, not
+ * HBM bound (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).                       */
+int nmpc_fma_peak_probe(int elem_size, double *tflops);
+
+/* ---- device model check: one evaluation of the reference callback per (problem, stage) -------
+ * Mirrors FORCESNLPsolver_normal_casadi2forces (solver/normal/FORCESNLPsolver_normal_casadi2forces.c:42-55)
+ * for n independent (z[17], p[130], stage) triples in HOST memory; dense COLUMN-major outputs:
+ * f[n], grad[n][17], c[n][13], jc[n][13*17], h[n][30], jh[n][30*17].                            */
+int nmpc_model_eval_host_f64(int n, const double *z, const double *p, const int *stage, int n_stages,
+                             int variant, double *f, double *grad, double *c, double *jc,
+                             double *h, double *jh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

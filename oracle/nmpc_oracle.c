@@ -453,7 +453,7 @@ static void evaluate(const work_t *w, real (*z)[NZ], real (*s)[MC_MAX], eval_t *
 }
 
 static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, const real *z0,
-                     real *z_out, int *iinfo, real *rinfo)
+                     real *z_out, int *iinfo, real *rinfo, real *y_out, real *zl_out, real *zu_out, real *lc_out)
 {
     const int N = w->N;
     const real eps = (sizeof(real) == 8) ? (real)2.220446049250313e-16 : (real)1.1920929e-07;
@@ -623,6 +623,12 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
         cur = 1 - cur;
     }
     for (int k = 0; k < N; k++) for (int i = 0; i < NZ; i++) z_out[k * NZ + i] = w->z[k][i];
+    for (int k = 0; k < N; k++) {
+        if (y_out) for (int i = 0; i < NXI; i++) y_out[k * NXI + i] = k ? w->y[k][i] : 0;
+        if (zl_out) for (int i = 0; i < NZ; i++) zl_out[k * NZ + i] = w->zl[k][i];
+        if (zu_out) for (int i = 0; i < NZ; i++) zu_out[k * NZ + i] = w->zu[k][i];
+        if (lc_out) for (int j = 0; j < w->mcap; j++) lc_out[k * w->mcap + j] = j < live_rows(w, k) ? w->lc[k][j] : 0;
+    }
     iinfo[0] = flag; iinfo[1] = it; iinfo[2] = nbt_total; iinfo[3] = 0;
     rinfo[0] = req_n; rinfo[1] = rin_n; rinfo[2] = rs_n; rinfo[3] = rcomp;
     rinfo[4] = w->ev[cur].f; rinfo[5] = mu; rinfo[6] = alpha_p; rinfo[7] = alpha_d;
@@ -632,6 +638,15 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
 int nmpc_oracle_solve_batch(int B, int N, int mcap, const real *xinit, const real *z0, const real *hdr,
                             const real *rows, const int *nrows, int variant, const nmpc_oracle_opts *opts,
                             real *z_out, int *info_int, real *info_real, int nthreads)
+{
+    return nmpc_oracle_solve_batch_ex(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int,
+                                      info_real, 0, 0, 0, 0, nthreads);
+}
+
+int nmpc_oracle_solve_batch_ex(int B, int N, int mcap, const real *xinit, const real *z0, const real *hdr,
+                               const real *rows, const int *nrows, int variant, const nmpc_oracle_opts *opts,
+                               real *z_out, int *info_int, real *info_real, real *y_out, real *zl_out,
+                               real *zu_out, real *lc_out, int nthreads)
 {
     if (N < 2 || N > NS_MAX || mcap < 0 || mcap > MC_MAX) return -11;
     nmpc_oracle_opts o;
@@ -651,7 +666,9 @@ int nmpc_oracle_solve_batch(int B, int N, int mcap, const real *xinit, const rea
             w->rows = rows + (size_t)b * N * mcap * 4;
             w->nrows = nrows + (size_t)b * N;
             solve_one(w, &o, xinit + (size_t)b * 9, z0 + (size_t)b * N * NZ, z_out + (size_t)b * N * NZ,
-                      info_int + (size_t)b * 4, info_real + (size_t)b * 8);
+                      info_int + (size_t)b * 4, info_real + (size_t)b * 8,
+                      y_out ? y_out + (size_t)b * N * NXI : 0, zl_out ? zl_out + (size_t)b * N * NZ : 0,
+                      zu_out ? zu_out + (size_t)b * N * NZ : 0, lc_out ? lc_out + (size_t)b * N * mcap : 0);
         }
         free(w);
     }

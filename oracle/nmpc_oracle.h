@@ -60,6 +60,14 @@ int nmpc_oracle_solve_batch(int B, int N, int mcap, const real *xinit, const rea
                             const nmpc_oracle_opts *opts, real *z_out, int *info_int,
                             real *info_real, int nthreads);
 
+/* same, also returning the multipliers of the KKT point (any may be NULL):
+ * y [B][N][13] (c-ordering, y[0]=0), zl / zu [B][N][17], lc [B][N][mcap]                  */
+int nmpc_oracle_solve_batch_ex(int B, int N, int mcap, const real *xinit, const real *z0,
+                               const real *hdr, const real *rows, const int *nrows, int variant,
+                               const nmpc_oracle_opts *opts, real *z_out, int *info_int,
+                               real *info_real, real *y_out, real *zl_out, real *zu_out,
+                               real *lc_out, int nthreads);
+
 /* One structured KKT solve (ForcesPro-style Schur complement, dense 17/13 blocks):
  *   min 1/2 dz' Phi dz + g' dz   s.t.  E dz_{k+1} = C_k dz_k + d_k ,  dz_0[8:17] = 0
  * Phi [N][17][17], g [N][17], C [N-1][13][17] (rows in c-ordering [x(9);u(4)]), d [N-1][13]

@@ -63,8 +63,9 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_batch(batch, dtype=np.float64, opts: OracleOpts | None = None, nthreads: int = 0):
-    """Solve a workloads.Batch on the CPU.  Returns dict(z, flag, it, nbt, info_real)."""
+def solve_batch(batch, dtype=np.float64, opts: OracleOpts | None = None, nthreads: int = 0,
+                multipliers: bool = False):
+    """Solve a workloads.Batch on the CPU.  Returns dict(z, flag, it, nbt, info_real[, y, zl, zu, lc])."""
     dtype = np.dtype(dtype)
     lib = _lib(dtype)
     B, N, mcap = batch.B, batch.N, batch.mcap
@@ -77,12 +78,18 @@ def solve_batch(batch, dtype=np.float64, opts: OracleOpts | None = None, nthread
     ii = np.zeros((B, 4), np.int32)
     ir = np.zeros((B, 8), dtype)
     o = opts or default_opts()
-    rc = lib.nmpc_oracle_solve_batch(B, N, mcap, _p(xinit), _p(z0), _p(hdr), _p(rows), _p(nrows),
-                                     int(batch.variant), ctypes.byref(o), _p(z), _p(ii), _p(ir),
-                                     int(nthreads))
+    y = np.zeros((B, N, 13), dtype); zl = np.zeros((B, N, 17), dtype); zu = np.zeros((B, N, 17), dtype)
+    lc = np.zeros((B, N, max(mcap, 1)), dtype)[:, :, :mcap].copy()
+    lib.nmpc_oracle_solve_batch_ex.restype = ctypes.c_int
+    rc = lib.nmpc_oracle_solve_batch_ex(B, N, mcap, _p(xinit), _p(z0), _p(hdr), _p(rows), _p(nrows),
+                                        int(batch.variant), ctypes.byref(o), _p(z), _p(ii), _p(ir),
+                                        _p(y), _p(zl), _p(zu), _p(lc) if mcap else None, int(nthreads))
     if rc != 0:
         raise ValueError(f"nmpc_oracle_solve_batch rejected the arguments (rc={rc})")
-    return dict(z=z, flag=ii[:, 0].copy(), it=ii[:, 1].copy(), nbt=ii[:, 2].copy(), info_real=ir)
+    out = dict(z=z, flag=ii[:, 0].copy(), it=ii[:, 1].copy(), nbt=ii[:, 2].copy(), info_real=ir)
+    if multipliers:
+        out.update(y=y, zl=zl, zu=zu, lc=lc)
+    return out
 
 
 def model_eval(z, p130, stage, n_stages=20, variant=0):

@@ -1,0 +1,95 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares; the
+reference ABI structs have the reference's exact layout; option defaults agree with the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+from forces_resilient_planner_b200 import _lib, forces
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for hdr in ("nmpc_b200.h", "FORCESNLPsolver_normal.h", "FORCESNLPsolver_final.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b((?:nmpc_|FORCESNLPsolver_(?:normal|final)_solve)\w*)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    declared = _declared_symbols()
+    assert {"nmpc_solve_batch_f64", "FORCESNLPsolver_normal_solve", "FORCESNLPsolver_final_solve",
+            "nmpc_kkt_backsolve_f64", "nmpc_pack_params_f64"} <= declared
+    missing = [s for s in sorted(declared) if not hasattr(cuda_lib, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) <= declared
+
+
+def test_reference_struct_layouts():
+    assert ctypes.sizeof(forces.ForcesParams) == 23600
+    assert forces.ForcesParams.xinit.offset == 0 and forces.ForcesParams.x0.offset == 72
+    assert forces.ForcesParams.all_parameters.offset == 2792 and forces.ForcesParams.num_of_threads.offset == 23592
+    assert ctypes.sizeof(forces.ForcesOutput) == 2720 and forces.ForcesOutput.x20.offset == 19 * 136
+    info = forces.ForcesInfo
+    assert ctypes.sizeof(info) == 136
+    names = ("it", "it2opt", "res_eq", "res_ineq", "rsnorm", "rcompnorm", "pobj", "dobj", "dgap", "rdgap", "mu",
+             "mu_aff", "sigma", "lsit_aff", "lsit_cc", "step_aff", "step_cc", "solvetime", "fevalstime")
+    assert [getattr(info, f).offset for f in names] == \
+        [0, 4, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 100, 104, 112, 120, 128]
+
+
+def test_headers_compile_as_c_and_cpp(tmp_path):
+    src = '#include "FORCESNLPsolver_normal.h"\n#include "FORCESNLPsolver_final.h"\n#include "nmpc_b200.h"\n' \
+          'int main(void){FORCESNLPsolver_normal_params p; FORCESNLPsolver_final_output o; (void)p; (void)o; ' \
+          'return sizeof(p)==23600 && sizeof(o)==2720 ? 0 : 1;}\n'
+    for ext, cc in ((".c", "gcc"), (".cpp", "g++")):
+        f = tmp_path / ("t" + ext)
+        f.write_text(src)
+        exe = tmp_path / ("t" + ext + ".out")
+        subprocess.check_call([f"/usr/bin/{cc}", "-I", os.path.join(ROOT, "include"), str(f), "-o", str(exe)])
+        assert subprocess.call([str(exe)]) == 0
+
+
+def test_default_options_match_the_oracle(cuda_lib):
+    a, b = _lib.default_opts(), O.default_opts()
+    for name, _ in _lib.NmpcOpts._fields_:
+        assert getattr(a, name) == getattr(b, name), name
+    assert a.maxit == 200 and a.tol_stat == a.tol_eq == a.tol_ineq == a.tol_comp == 1e-4
+
+
+def test_metadata_calls_work_without_a_gpu(cuda_lib):
+    assert cuda_lib.nmpc_supported_horizon(20) == 1 and cuda_lib.nmpc_supported_horizon(40) == 1
+    assert cuda_lib.nmpc_supported_horizon(21) == 0
+    assert 40_000 < cuda_lib.nmpc_smem_bytes(20, 8, 8) < 60_000
+    assert cuda_lib.nmpc_backsolve_factor_words() == 204
+    assert b"sm_100a" in cuda_lib.nmpc_version()
+
+
+def test_no_cpu_fallback_without_a_device(cuda_lib):
+    """On a machine without a GPU the solve entry points must fail loudly, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from forces_resilient_planner_b200 import solver as S, workloads as W
+    try:
+        S.solve_host(W.config2(2))
+    except RuntimeError as e:
+        assert "rc=-101" in str(e)
+    else:
+        raise AssertionError("solve_host computed something without a GPU")
+    w = forces.FORCESNormal()
+    assert w.solve_params() == -101
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "forces_resilient_planner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, fn
+                assert "libnmpc_oracle" not in txt and not re.search(r'#include\s*[<"][^>"]*oracle', txt), fn

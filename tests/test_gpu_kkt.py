@@ -1,0 +1,117 @@
+"""Stand-alone Riccati factor + KKT backsolve kernels and the pack / shift kernels, against the
+oracle's Schur-complement solve and numpy restatements.  All need a GPU."""
+import numpy as np
+import pytest
+
+from forces_resilient_planner_b200 import kkt, prep, workloads as W
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.mark.parametrize("N", [20, 40])
+def test_factor_and_backsolve_match_schur_oracle(N):
+    import torch
+    B = 37
+    phi, jc, g, d = kkt.random_kkt_problems(B, N, seed=N)
+    fac, status = kkt.riccati_factor(_t(phi), _t(jc))
+    assert torch.all(status == 0)
+    dz, y = kkt.kkt_backsolve(fac, _t(g), _t(d))
+    dz, y = dz.cpu().numpy(), y.cpu().numpy()
+    for b in range(0, B, 6):
+        Phi, C = kkt.dense_from_compact(phi[b], jc[b])
+        rc, dz_ref, y_ref = O.kkt_solve(Phi, g[b], C, d[b, :N - 1])
+        assert rc == 0
+        assert np.max(np.abs(dz[b] - dz_ref)) < 1e-9 * max(1.0, np.max(np.abs(dz_ref)))
+        assert np.max(np.abs(y[b, 1:] - y_ref[1:])) < 1e-8 * max(1.0, np.max(np.abs(y_ref)))
+        assert np.all(y[b, 0] == 0) and np.all(dz[b, 0, 8:17] == 0)
+
+
+def test_backsolve_is_linear_in_the_rhs_and_reuses_the_factor():
+    """Size-independent property at the bench size: one factor, many right-hand sides."""
+    import torch
+    B, N = 4096, 20
+    phi, jc, g, d = kkt.random_kkt_problems(B, N, seed=7)
+    fac, status = kkt.riccati_factor(_t(phi), _t(jc))
+    assert torch.all(status == 0)
+    g1, d1 = _t(g), _t(d)
+    g2, d2 = _t(np.roll(g, 1, axis=0)), _t(np.roll(d, 1, axis=0))
+    z1, y1 = kkt.kkt_backsolve(fac, g1, d1)
+    z2, y2 = kkt.kkt_backsolve(fac, g2, d2)
+    z3, y3 = kkt.kkt_backsolve(fac, 2.0 * g1 - 0.5 * g2, 2.0 * d1 - 0.5 * d2)
+    scale = float(z1.abs().max())
+    assert float((z3 - (2.0 * z1 - 0.5 * z2)).abs().max()) < 1e-10 * scale
+    assert float((y3 - (2.0 * y1 - 0.5 * y2)).abs().max()) < 1e-9 * float(y1.abs().max())
+    # residual of the KKT system itself for a few problems: Phi dz + g + J'y+ - E'y = 0, E dz+ = J dz + d
+    z1n, y1n = z1.cpu().numpy(), y1.cpu().numpy()
+    for b in (0, 1234, 4095):
+        Phi, C = kkt.dense_from_compact(phi[b], jc[b])
+        for k in range(N):
+            r = Phi[k] @ z1n[b, k] + g[b, k]
+            if k < N - 1:
+                r += C[k].T @ y1n[b, k + 1]
+                e = np.concatenate([z1n[b, k + 1, 8:17], z1n[b, k + 1, 4:8]]) - C[k] @ z1n[b, k] - d[b, k]
+                assert np.max(np.abs(e)) < 1e-10
+            if k > 0:
+                r[8:17] -= y1n[b, k, 0:9]; r[4:8] -= y1n[b, k, 9:13]
+                assert np.max(np.abs(r)) < 1e-8
+            else:
+                assert np.max(np.abs(r[:8])) < 1e-8
+
+
+def test_backsolve_fp32_within_tolerance():
+    import torch
+    B, N = 64, 20
+    phi, jc, g, d = kkt.random_kkt_problems(B, N, seed=3)
+    f64, _ = kkt.riccati_factor(_t(phi), _t(jc))
+    z64, _ = kkt.kkt_backsolve(f64, _t(g), _t(d))
+    f32, st = kkt.riccati_factor(_t(phi, torch.float32), _t(jc, torch.float32))
+    assert torch.all(st == 0)
+    z32, _ = kkt.kkt_backsolve(f32, _t(g, torch.float32), _t(d, torch.float32))
+    # stated fp32 tolerance: 1e-4 relative to the largest step component
+    assert float((z32.double() - z64).abs().max()) < 1e-4 * float(z64.abs().max())
+
+
+def test_factor_flags_indefinite_blocks():
+    import torch
+    phi, jc, g, d = kkt.random_kkt_problems(3, 20, seed=1)
+    phi[1, 5, 0:4] = -1e3          # negative curvature in the input block of one stage
+    _, status = kkt.riccati_factor(_t(phi), _t(jc))
+    assert status.cpu().tolist() == [0, -5, 0]
+
+
+def test_pack_params_matches_reference_loop():
+    rng = np.random.default_rng(0)
+    B, N, P, M, mcap = 33, 20, 3, 40, 30          # polytopes with more rows than the capacity: truncated at 30
+    ref_pos = rng.normal(size=(B, N, 3)); ref_yaw = rng.normal(size=(B, N)); ext = rng.normal(size=(B, 3))
+    Emat = rng.normal(size=(B, N, 9)) * 0.3
+    A = rng.normal(size=(B, P, M, 3)); A /= np.linalg.norm(A, axis=-1, keepdims=True)
+    bb = rng.uniform(0.5, 3, (B, P, M)); pm = rng.integers(0, M + 1, (B, P)).astype(np.int32)
+    pidx = rng.integers(0, P, (B, N)).astype(np.int32)
+    w5 = (7.0, 1.0, 80.0, 12.0, 0.5)
+    hdr, rows, nrows = prep.pack_params(_t(ref_pos), _t(ref_yaw), _t(ext), _t(Emat), _t(A), _t(bb), _t(pm), _t(pidx), w5, mcap)
+    h0, r0, n0 = prep.pack_params_reference(ref_pos, ref_yaw, ext, Emat, A, bb, pm, pidx, w5, mcap)
+    assert np.array_equal(nrows.cpu().numpy(), n0) and n0.max() == 30
+    assert np.array_equal(hdr.cpu().numpy(), h0)
+    assert np.max(np.abs(rows.cpu().numpy() - r0)) < 1e-14
+
+
+def test_shift_warm_start_matches_reference_shift():
+    rng = np.random.default_rng(1)
+    z = rng.normal(size=(50, 20, 17)); z[:, :, 16] = rng.uniform(-2 * np.pi, 2 * np.pi, (50, 20))
+    xinit, z0 = prep.shift_warm_start(_t(z), wrap_yaw=False)
+    x_ref, z_ref = W.shift_warm_start(z)
+    assert np.array_equal(z0.cpu().numpy(), z_ref) and np.array_equal(xinit.cpu().numpy(), x_ref)
+    xinit, z0 = prep.shift_warm_start(_t(z), wrap_yaw=True)
+    zw = z.copy(); yaw = zw[:, :, 16]
+    zw[:, :, 16] = np.where(yaw < -np.pi, yaw + 2 * np.pi, np.where(yaw > np.pi, yaw - 2 * np.pi, yaw))
+    x_ref, z_ref = W.shift_warm_start(zw)
+    assert np.allclose(z0.cpu().numpy(), z_ref, atol=0, rtol=0) and np.array_equal(xinit.cpu().numpy(), x_ref)

@@ -1,0 +1,193 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, the committed
+golden fixtures and size-independent properties.  All need a GPU."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from forces_resilient_planner_b200 import _lib, forces, solver as S, workloads as W
+from oracle import oracle as O
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GOLD_DIR = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _model(variant=0):
+    if ref_model.available():
+        return ref_model.RefModel("final" if variant else "normal").eval
+    return lambda z, p, k: O.model_eval(z, p, k, 20, variant)
+
+
+def _compare(g, c, frac_same_it=0.85, tol_z=2e-4, tol_z_median=1e-6):
+    """GPU (Riccati) vs oracle (Schur complement): same exit flags, same KKT point.
+
+    The two factorizations round differently, so the iterate paths separate at the 1e-9 level
+    and an iteration count can differ by one when a residual lands next to its 1e-4 threshold;
+    the converged points then differ by at most the stopping tolerance."""
+    assert np.array_equal(g.flag, c["flag"])
+    dz = np.abs(g.z - c["z"]).reshape(g.z.shape[0], -1).max(1)
+    assert dz.max() < tol_z and np.median(dz) < tol_z_median
+    assert np.mean(g.it == c["it"]) >= frac_same_it and np.max(np.abs(g.it - c["it"])) <= 3
+
+
+def test_device_model_matches_reference_vectors():
+    cases = json.load(open(os.path.join(GOLD_DIR, "model_vectors.json")))["cases"]
+    for variant in ("normal", "final"):
+        cs = [c for c in cases if c["variant"] == variant]
+        z = np.array([c["z"] for c in cs]); p = np.array([c["p"] for c in cs])
+        st = np.array([c["stage"] for c in cs], np.int32)
+        r = S.model_eval_device(z, p, st, 20, 1 if variant == "final" else 0)
+        for i, c in enumerate(cs):
+            rel = lambda a, b: np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(1, np.abs(np.asarray(b))), initial=0)
+            assert rel(r["f"][i], c["f"]) < 1e-12 and rel(r["grad"][i], c["grad"]) < 1e-12
+            if c["stage"] < 19:
+                assert rel(r["c"][i], c["c"]) < 1e-12 and rel(r["jc"][i], c["jc"]) < 1e-12
+            jh = np.zeros((30, 17))
+            for a, b, v in c["jh_nnz"]:
+                jh[a, b] = v
+            assert rel(r["h"][i], c["h"]) < 1e-12 and rel(r["jh"][i], jh) < 1e-12
+
+
+def test_config1_anchor_and_golden_solution():
+    gold = json.load(open(os.path.join(GOLD_DIR, "config1_solution.json")))
+    g = S.solve_host(W.config1())
+    assert g.flag[0] == 1 and g.it[0] == gold["it"]
+    assert np.max(np.abs(g.z[0] - np.array(gold["z"]))) < 1e-6
+    assert abs(g.info_real[0, 4] - gold["pobj"]) < 1e-6
+
+
+@pytest.mark.parametrize("maker,kw", [(W.config2, dict(B=512)), (W.config3, dict(B=512)),
+                                      (W.config2, dict(B=128, variant=1)), (W.config4, dict(side=12, n_stages=40))])
+def test_gpu_matches_oracle(maker, kw):
+    b = maker(**kw)
+    _compare(S.solve_host(b), O.solve_batch(b))
+
+
+def test_device_pointer_api_equals_host_pointer_api():
+    b = W.config2(300)
+    a, c = S.solve(b), S.solve_host(b)
+    assert np.array_equal(a.z, c.z) and np.array_equal(a.flag, c.flag) and np.array_equal(a.it, c.it)
+
+
+def test_kkt_point_passes_forcespro_acceptance_with_reference_callbacks():
+    for b in (W.config2(64), W.config3(64), W.config2(32, variant=1)):
+        res, mult = S.solve_with_multipliers(b)
+        assert np.all(res.flag == 1)
+        model = _model(b.variant)
+        for i in range(0, b.B, 4):
+            r = H.kkt_residuals(b, i, res.z[i], mult["y"][i], mult["zl"][i], mult["zu"][i], mult["lc"][i], model)
+            assert max(r) <= TOL, (i, r)
+            assert abs(r[0] - res.info_real[i, 2]) < 1e-6      # self-reported rsnorm is honest
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (B=4096): everything converges inside the iteration cap and
+    the size-independent properties hold (feasibility, bounds, fixed initial state, idempotence)."""
+    b = W.config2(4096)
+    g = S.solve_host(b)
+    assert np.all(g.flag == 1) and g.it.max() <= 40
+    assert np.all(g.info_real[:, 0:4] <= TOL)
+    assert np.array_equal(g.z[:, 0, 8:17], b.xinit)
+    from oracle import model_np as M
+    assert np.all(g.z >= M.LB - 1e-9) and np.all(g.z <= M.UB + 1e-9)
+    viol = np.einsum("bkmj,bkj->bkm", b.rows[:, 1:, :, 0:3], g.z[:, 1:, 8:11]) - b.rows[:, 1:, :, 3] - 1e-5
+    assert viol.max() <= TOL
+    # u_prev chain: z_{k+1}[4:8] = z_k[0:4]
+    assert np.max(np.abs(g.z[:, 1:, 4:8] - g.z[:, :-1, 0:4])) <= TOL
+    # idempotence: restarting from the solution stays at the solution
+    b2 = W.Batch(b.xinit, g.z.copy(), b.hdr, b.rows, b.nrows, b.variant)
+    g2 = S.solve_host(b2)
+    assert np.all(g2.flag == 1)
+    assert np.max(np.abs(g2.z - g.z)) < 5e-3 and np.median(np.abs(g2.z - g.z).reshape(b.B, -1).max(1)) < 1e-4
+
+
+def test_forces_abi_shim_matches_batch_api():
+    """FORCESNLPsolver_normal_solve / _final_solve with the reference's padded 130-slot layout."""
+    for variant, cls in ((0, forces.FORCESNormal), (1, forces.FORCESFinal)):
+        b = W.config2(3, variant=variant)
+        ref = S.solve_host(b)
+        w = cls()
+        for i in range(b.B):
+            xinit, x0, allp = W.to_forces_params(b, i)
+            w.params_.xinit[:] = xinit.tolist(); w.params_.x0[:] = x0.tolist()
+            w.params_.all_parameters[:] = allp.tolist()
+            flag = w.solve_params()
+            assert flag == 1 == ref.flag[i]
+            assert np.max(np.abs(w.output_array() - ref.z[i])) < 1e-12
+            assert w.info_.it == ref.it[i] and w.info_.solvetime > 0
+            assert abs(w.info_.pobj - ref.info_real[i, 4]) < 1e-12 and w.info_.rsnorm <= TOL
+
+
+def test_reference_wrapper_flow_solveNormal_updateNormal():
+    """The planner's own call sequence (nmpc_solver.cpp:384,421): setParas -> solve -> update."""
+    b = W.config1()
+    w = forces.FORCESNormal()
+    w.setParasNormal(7.0, 1.0, 80.0, 12.0, 0.5)
+    mpc_output = [np.array(b.z0[0, 0]) for _ in range(21)]            # initMPCOutput
+    A = b.rows[0, 1, :6, 0:3]; braw = b.rows[0, 1, :6, 3] + np.linalg.norm(A * W.EGO_E, axis=1)
+    E = np.diag(W.EGO_E)
+    flag = w.solveNormal(mpc_output, [0.0, 0.0, 0.0], [b.hdr[0, k, 0:3] for k in range(20)],
+                         [b.hdr[0, k, 9] for k in range(20)], [E] * 20, [(A, braw)], np.zeros(20))
+    assert flag == 1
+    w.updateNormal(mpc_output)
+    direct = S.solve_host(b)
+    assert np.max(np.abs(np.array(mpc_output[:20]) - direct.z[0])) < 1e-9
+
+
+def test_edge_cases_rows_and_batch_sizes():
+    assert S.solve_host(W.config2(0)).z.shape == (0, 20, 17)             # empty batch
+    b = W.config2(5)
+    b0 = W.Batch(b.xinit, b.z0, b.hdr, np.zeros((5, 20, 0, 4)), np.zeros((5, 20), np.int32))   # no corridor at all
+    r0 = S.solve_host(b0); c0 = O.solve_batch(b0)
+    assert np.all(r0.flag == 1) and np.max(np.abs(r0.z - c0["z"])) < 1e-4
+    # ragged: a different live-row count at every stage, capacity 32 (the ABI maximum is 30 rows)
+    rng = np.random.default_rng(0)
+    b = W.config3(64, mcap=32)
+    b.nrows[:] = np.minimum(b.nrows, rng.integers(0, 11, b.nrows.shape)).astype(np.int32)
+    _compare(S.solve_host(b), O.solve_batch(b))
+    # nrows larger than mcap is clamped, not read out of bounds
+    b = W.config2(4); b.nrows[:] = 99
+    c = W.config2(4); c.nrows[:] = c.mcap
+    assert np.array_equal(S.solve_host(b).z, S.solve_host(c).z)
+
+
+def test_failure_flags():
+    b = W.config2(6)
+    b.hdr[0, 3, 0] = np.nan                                   # NaN in a function evaluation -> -6
+    b.xinit[1, 3:6] = [1.5, 0, 0]; b.z0[1, :, 11:14] = [1.5, 0, 0]
+    b.rows[1, :, 0, 0:3] = [1.0, 0, 0]; b.rows[1, :, 0, 3] = b.xinit[1, 0] + 0.05   # wall: infeasible
+    g = S.solve_host(b, opts=_lib.default_opts(maxit=60))
+    c = O.solve_batch(b, opts=O.default_opts(maxit=60))
+    assert g.flag[0] in (-6, -7) and g.flag[1] != 1
+    assert np.all(g.flag[2:] == 1)                            # a failing instance never stalls the others
+    assert np.array_equal(g.flag[2:], c["flag"][2:])
+
+
+def test_bad_arguments_are_rejected_loudly():
+    lib = _lib.load()
+    b = W.config2(2)
+    x = np.zeros(4)
+    rc = lib.nmpc_solve_batch_host_f64(2, 21, 8, x.ctypes.data, x.ctypes.data, x.ctypes.data, x.ctypes.data,
+                                       x.ctypes.data, 0, None, x.ctypes.data, x.ctypes.data, x.ctypes.data)
+    assert rc == -11 and b"N=21" in lib.nmpc_last_error()
+    with pytest.raises(RuntimeError):
+        S.solve_host(W.Batch(b.xinit, b.z0, b.hdr, np.zeros((2, 20, 40, 4)), b.nrows))   # mcap > 32
+
+
+def test_warm_start_shift_uses_fewer_iterations():
+    b = W.config2(256)
+    g = S.solve_host(b)
+    xinit, z0 = W.shift_warm_start(g.z)
+    hdr = b.hdr.copy()
+    hdr[:, :-1, 0:3] = b.hdr[:, 1:, 0:3]; hdr[:, -1, 0:3] = 2 * b.hdr[:, -1, 0:3] - b.hdr[:, -2, 0:3]
+    hdr[:, :-1, 9] = b.hdr[:, 1:, 9]
+    b2 = W.Batch(xinit, z0, hdr, b.rows, b.nrows, b.variant)
+    g2 = S.solve_host(b2, opts=_lib.default_opts(mu0=0.1))
+    c2 = O.solve_batch(b2, opts=O.default_opts(mu0=0.1))
+    assert np.all(g2.flag == 1) and g2.it.mean() < g.it.mean()
+    _compare(g2, c2)
