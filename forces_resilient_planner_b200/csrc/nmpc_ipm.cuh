@@ -792,7 +792,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         s.step_lengths(mu_t, tau, ap, ad);
         // backtracking line search on (theta, barrier objective)
         const T ph0 = f_cur - mu_t * ls_cur;
-        const T th_noise = T(10) * Eps<T>::v * T(N * NXI) * T(20);
+        // theta below 1% of TolEq counts as feasible (also absorbs the rounding floor of theta)
+        const T th_noise = fmax(T(10) * Eps<T>::v * T(N * NXI) * T(20), T(0.01) * (T)o.tol_eq);
         T a = ap;
         int nbt = 0;
         for (;;) {

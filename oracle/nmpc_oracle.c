@@ -272,97 +272,141 @@ static inline int e_col(int i) { return i < 9 ? 8 + i : i - 9 + 4; }
  *   Phi dz + A' y = -g,   A dz = -d,   row block k (1..N-1):  C_{k-1} dz_{k-1} - E dz_k = -d_{k-1}
  * Stage-0 fixed variables must already be decoupled by the caller (identity rows, zero g, zero C cols).
  */
-static int kkt_solve(int N, real (*Phi)[NZ][NZ], real (*g)[NZ], real (*C)[NXI][NZ], real (*d)[NXI],
-                     real (*dz)[NZ], real (*y)[NXI])
-{
-    static _Thread_local real L[NS_MAX][NZ][NZ];
-    static _Thread_local real V[NS_MAX][NXI][NZ];   /* V_k = C_k L_k^-T            (k = 0..N-2) */
-    static _Thread_local real W[NS_MAX][NXI][NZ];   /* W_k = D   L_k^-T, D = -E    (k = 1..N-1) */
-    static _Thread_local real Yd[NS_MAX][NXI][NXI]; /* diagonal blocks -> their Cholesky factors */
-    static _Thread_local real Yo[NS_MAX][NXI][NXI]; /* Yo[k] = Y_{k+1,k} -> L_{k+1,k}            */
-    static _Thread_local real t[NS_MAX][NZ];        /* L_k^-1 g_k                                */
-    static _Thread_local real beta[NS_MAX][NXI];
+/* factor storage (per thread) */
+static _Thread_local real kL[NS_MAX][NZ][NZ];
+static _Thread_local real kV[NS_MAX][NXI][NZ];   /* V_k = C_k L_k^-T            (k = 0..N-2) */
+static _Thread_local real kW[NS_MAX][NXI][NZ];   /* W_k = D   L_k^-T, D = -E    (k = 1..N-1) */
+static _Thread_local real kYd[NS_MAX][NXI][NXI]; /* Cholesky factors of the Schur diagonal     */
+static _Thread_local real kYo[NS_MAX][NXI][NXI]; /* L_{k+1,k}                                  */
 
+static int kkt_factor(int N, real (*Phi)[NZ][NZ], real (*C)[NXI][NZ])
+{
     for (int k = 0; k < N; k++) {
-        memcpy(L[k], Phi[k], sizeof(real) * NZ * NZ);
-        if (chol(NZ, &L[k][0][0], NZ)) return -5;
-        for (int i = 0; i < NZ; i++) t[k][i] = g[k][i];
-        fsub(NZ, &L[k][0][0], NZ, t[k]);
+        memcpy(kL[k], Phi[k], sizeof(real) * NZ * NZ);
+        if (chol(NZ, &kL[k][0][0], NZ)) return -5;
         if (k < N - 1)
             for (int r = 0; r < NXI; r++) {
-                memcpy(V[k][r], C[k][r], sizeof(real) * NZ);
-                fsub(NZ, &L[k][0][0], NZ, V[k][r]);
+                memcpy(kV[k][r], C[k][r], sizeof(real) * NZ);
+                fsub(NZ, &kL[k][0][0], NZ, kV[k][r]);
             }
         if (k > 0)
             for (int r = 0; r < NXI; r++) {
-                memset(W[k][r], 0, sizeof(real) * NZ);
-                W[k][r][e_col(r)] = -1;
-                fsub(NZ, &L[k][0][0], NZ, W[k][r]);
+                memset(kW[k][r], 0, sizeof(real) * NZ);
+                kW[k][r][e_col(r)] = -1;
+                fsub(NZ, &kL[k][0][0], NZ, kW[k][r]);
             }
     }
-    /* Schur complement Y = A Phi^-1 A' (block tridiagonal), rhs beta = d - A Phi^-1 g */
+    /* Schur complement Y = A Phi^-1 A' (block tridiagonal) */
     for (int k = 1; k < N; k++) {
-        for (int i = 0; i < NXI; i++) {
+        for (int i = 0; i < NXI; i++)
             for (int j = 0; j <= i; j++) {
                 real s = 0;
-                for (int q = 0; q < NZ; q++) s += V[k - 1][i][q] * V[k - 1][j][q] + W[k][i][q] * W[k][j][q];
-                Yd[k][i][j] = Yd[k][j][i] = s;
+                for (int q = 0; q < NZ; q++) s += kV[k - 1][i][q] * kV[k - 1][j][q] + kW[k][i][q] * kW[k][j][q];
+                kYd[k][i][j] = kYd[k][j][i] = s;
             }
-            real b = d[k - 1][i];
-            for (int q = 0; q < NZ; q++) b -= V[k - 1][i][q] * t[k - 1][q] + W[k][i][q] * t[k][q];
-            beta[k][i] = b;
-        }
         if (k < N - 1) /* Y_{k+1,k} = C_k Phi_k^-1 D' = V_k W_k' */
             for (int i = 0; i < NXI; i++)
                 for (int j = 0; j < NXI; j++) {
                     real s = 0;
-                    for (int q = 0; q < NZ; q++) s += V[k][i][q] * W[k][j][q];
-                    Yo[k][i][j] = s;
+                    for (int q = 0; q < NZ; q++) s += kV[k][i][q] * kW[k][j][q];
+                    kYo[k][i][j] = s;
                 }
     }
-    /* block-tridiagonal Cholesky + forward substitution */
+    /* block-tridiagonal Cholesky */
     for (int k = 1; k < N; k++) {
         if (k > 1) {
-            /* L_{k,k-1} = Y_{k,k-1} L_{k-1,k-1}^-T  (row-wise forward substitution) */
-            for (int i = 0; i < NXI; i++) fsub(NXI, &Yd[k - 1][0][0], NXI, Yo[k - 1][i]);
-            for (int i = 0; i < NXI; i++) {
+            for (int i = 0; i < NXI; i++) fsub(NXI, &kYd[k - 1][0][0], NXI, kYo[k - 1][i]);
+            for (int i = 0; i < NXI; i++)
                 for (int j = 0; j <= i; j++) {
                     real s = 0;
-                    for (int q = 0; q < NXI; q++) s += Yo[k - 1][i][q] * Yo[k - 1][j][q];
-                    Yd[k][i][j] -= s;
-                    if (j != i) Yd[k][j][i] -= s;
+                    for (int q = 0; q < NXI; q++) s += kYo[k - 1][i][q] * kYo[k - 1][j][q];
+                    kYd[k][i][j] -= s;
+                    if (j != i) kYd[k][j][i] -= s;
                 }
-                real s = 0;
-                for (int q = 0; q < NXI; q++) s += Yo[k - 1][i][q] * beta[k - 1][q];
-                beta[k][i] -= s;
-            }
         }
-        if (chol(NXI, &Yd[k][0][0], NXI)) return -5;
-        fsub(NXI, &Yd[k][0][0], NXI, beta[k]);
+        if (chol(NXI, &kYd[k][0][0], NXI)) return -5;
     }
-    /* backward substitution -> y */
+    return 0;
+}
+
+/* solve  Phi dz + A' y = -g,  A dz = -d  with the stored factor */
+static void kkt_solve_rhs(int N, real (*g)[NZ], real (*d)[NXI], real (*dz)[NZ], real (*y)[NXI])
+{
+    static _Thread_local real t[NS_MAX][NZ];
+    static _Thread_local real beta[NS_MAX][NXI];
+    for (int k = 0; k < N; k++) {
+        for (int i = 0; i < NZ; i++) t[k][i] = g[k][i];
+        fsub(NZ, &kL[k][0][0], NZ, t[k]);
+    }
+    for (int k = 1; k < N; k++) {
+        for (int i = 0; i < NXI; i++) {
+            real b = d[k - 1][i];
+            for (int q = 0; q < NZ; q++) b -= kV[k - 1][i][q] * t[k - 1][q] + kW[k][i][q] * t[k][q];
+            if (k > 1) for (int q = 0; q < NXI; q++) b -= kYo[k - 1][i][q] * beta[k - 1][q];
+            beta[k][i] = b;
+        }
+        fsub(NXI, &kYd[k][0][0], NXI, beta[k]);
+    }
     for (int k = N - 1; k >= 1; k--) {
         if (k < N - 1)
             for (int i = 0; i < NXI; i++) {
                 real s = 0;
-                for (int q = 0; q < NXI; q++) s += Yo[k][q][i] * y[k + 1][q];
+                for (int q = 0; q < NXI; q++) s += kYo[k][q][i] * y[k + 1][q];
                 beta[k][i] -= s;
             }
-        bsub(NXI, &Yd[k][0][0], NXI, beta[k]);
+        bsub(NXI, &kYd[k][0][0], NXI, beta[k]);
         for (int i = 0; i < NXI; i++) y[k][i] = beta[k][i];
     }
     for (int i = 0; i < NXI; i++) y[0][i] = 0;
-    /* dz_k = -Phi_k^-1 (g_k + C_k' y_{k+1} + D' y_k) = -L^-T (t_k + V_k' y_{k+1} + W_k' y_k) */
     for (int k = 0; k < N; k++) {
         real r[NZ];
         for (int q = 0; q < NZ; q++) {
             real s = t[k][q];
-            if (k < N - 1) for (int i = 0; i < NXI; i++) s += V[k][i][q] * y[k + 1][i];
-            if (k > 0) for (int i = 0; i < NXI; i++) s += W[k][i][q] * y[k][i];
+            if (k < N - 1) for (int i = 0; i < NXI; i++) s += kV[k][i][q] * y[k + 1][i];
+            if (k > 0) for (int i = 0; i < NXI; i++) s += kW[k][i][q] * y[k][i];
             r[q] = -s;
         }
-        bsub(NZ, &L[k][0][0], NZ, r);
+        bsub(NZ, &kL[k][0][0], NZ, r);
         for (int q = 0; q < NZ; q++) dz[k][q] = r[q];
+    }
+}
+
+/*
+ * Structured KKT solve.  Phi [N][17][17] SPD, g [N][17], C [N-1][13][17], d [N-1][13].
+ *   Phi dz + A' y = -g,   A dz = -d,   row block k (1..N-1):  C_{k-1} dz_{k-1} - E dz_k = -d_{k-1}
+ * Stage-0 fixed variables must already be decoupled by the caller (identity rows, zero g, zero C cols).
+ * The normal-equations route squares the conditioning of Phi (barrier terms reach 1e8), so the
+ * solution is polished by iterative refinement on the original saddle-point system.
+ */
+static int kkt_solve(int N, real (*Phi)[NZ][NZ], real (*g)[NZ], real (*C)[NXI][NZ], real (*d)[NXI],
+                     real (*dz)[NZ], real (*y)[NXI])
+{
+    static _Thread_local real rg[NS_MAX][NZ], rd[NS_MAX][NXI], cz[NS_MAX][NZ], cy[NS_MAX][NXI];
+    int rc = kkt_factor(N, Phi, C);
+    if (rc) return rc;
+    kkt_solve_rhs(N, g, d, dz, y);
+    for (int pass = 0; pass < 2; pass++) {
+        /* residuals: rg = g + Phi dz + A' y ,  rd = d + A dz  (both should be 0) */
+        for (int k = 0; k < N; k++) {
+            for (int i = 0; i < NZ; i++) {
+                real s = g[k][i];
+                for (int j = 0; j < NZ; j++) s += Phi[k][i][j] * dz[k][j];
+                if (k < N - 1) for (int r = 0; r < NXI; r++) s += C[k][r][i] * y[k + 1][r];
+                rg[k][i] = s;
+            }
+            if (k > 0) for (int r = 0; r < NXI; r++) rg[k][e_col(r)] -= y[k][r];
+            if (k < N - 1)
+                for (int r = 0; r < NXI; r++) {
+                    real s = d[k][r] - dz[k + 1][e_col(r)];
+                    for (int j = 0; j < NZ; j++) s += C[k][r][j] * dz[k][j];
+                    rd[k][r] = s;
+                }
+        }
+        kkt_solve_rhs(N, rg, rd, cz, cy);
+        for (int k = 0; k < N; k++) {
+            for (int i = 0; i < NZ; i++) dz[k][i] += cz[k][i];
+            for (int i = 0; i < NXI; i++) y[k][i] += cy[k][i];
+        }
     }
     return 0;
 }
@@ -590,7 +634,8 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
         }
         /* ---- backtracking line search on (theta, barrier objective) */
         real th0 = e->theta, ph0 = e->f - mu_t * e->logsum;
-        real th_noise = 10 * eps * (real)(N * NXI) * 20;
+        /* theta below 1% of TolEq counts as feasible (also absorbs the rounding floor of theta) */
+        real th_noise = fmax(10 * eps * (real)(N * NXI) * 20, (real)0.01 * (real)o->tol_eq);
         real a = ap;
         int nbt = 0;
         eval_t *tr = &w->ev[1 - cur];
