@@ -23,16 +23,17 @@ def _model(variant=0):
     return lambda z, p, k: O.model_eval(z, p, k, 20, variant)
 
 
-def _compare(g, c, frac_same_it=0.85, tol_z=2e-4, tol_z_median=1e-6):
-    """GPU (Riccati) vs oracle (Schur complement): same exit flags, same KKT point.
+def _compare(g, c, frac_same_it=0.99, tol_z=1e-4, tol_z_typical=1e-9):
+    """GPU (Riccati) vs oracle (Schur complement + refinement): same exit flags, same iterates.
 
-    The two factorizations round differently, so the iterate paths separate at the 1e-9 level
-    and an iteration count can differ by one when a residual lands next to its 1e-4 threshold;
-    the converged points then differ by at most the stopping tolerance."""
+    fp64 tolerance, stated: the two factorizations round differently, yet the iterate paths stay
+    together to ~1e-13, so >= 99 % of the problems must agree to 1e-9 with identical iteration
+    counts.  The remainder may take one iteration more or less when a residual lands next to its
+    1e-4 threshold; those points then differ by at most the stopping tolerance (1e-4)."""
     assert np.array_equal(g.flag, c["flag"])
     dz = np.abs(g.z - c["z"]).reshape(g.z.shape[0], -1).max(1)
-    assert dz.max() < tol_z and np.median(dz) < tol_z_median
-    assert np.mean(g.it == c["it"]) >= frac_same_it and np.max(np.abs(g.it - c["it"])) <= 3
+    assert dz.max() < tol_z and np.quantile(dz, 0.99) < tol_z_typical
+    assert np.mean(g.it == c["it"]) >= frac_same_it and np.max(np.abs(g.it - c["it"])) <= 1
 
 
 def test_device_model_matches_reference_vectors():
