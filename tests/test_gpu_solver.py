@@ -192,3 +192,13 @@ def test_warm_start_shift_uses_fewer_iterations():
     c2 = O.solve_batch(b2, opts=O.default_opts(mu0=0.1))
     assert np.all(g2.flag == 1) and g2.it.mean() < g.it.mean()
     _compare(g2, c2)
+
+
+def test_cpp_dropin_demo_runs_the_planner_call_sequence():
+    """host/dropin_demo.cpp: FORCESNormal/FORCESFinal (C++ mirror of forces_normal.cpp) against the .so."""
+    import subprocess
+    host = os.path.join(os.path.dirname(GOLD_DIR), "..", "forces_resilient_planner_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    out = subprocess.run([os.path.join(host, "dropin_demo")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("exitflag 1") == 4
