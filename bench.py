@@ -78,7 +78,10 @@ def cpu_baseline_run(batch, steps, warmup, nthreads=0):
     """Times oracle/ (test infrastructure; allowed here only as the measured baseline)."""
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() if nthreads <= 0 else nthreads
+    # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the baseline
+    if nthreads <= 0:
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = nthreads
     for _ in range(warmup):
         O.solve_batch(batch, nthreads=nthreads)
     times, res = [], None
