@@ -156,16 +156,16 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
 
     // stage 0: x fixed, u_prev free: dq = -Pqq^-1 p_q
     {
-        T a[16], l[10], x[4];
+        T a[16], l[10], li[4], x[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) a[4 * r + c] = FAC[pk(9 + r, 9 + c)];
+            for (int c = 0; c <= r; c++) a[4 * r + c] = FAC[pk(9 + r, 9 + c)];
             x[r] = -PV[9 + r];
         }
-        chol4<T>(a, l);
-        fsub4<T>(l, x);
-        bsub4<T>(l, x);
+        chol4<T>(a, l, li);
+        fsub4<T>(l, li, x);
+        bsub4<T>(l, li, x);
         if (lane < NXI) DXI[lane] = (lane < 9) ? T(0) : x[lane - 9];
     }
     __syncwarp();

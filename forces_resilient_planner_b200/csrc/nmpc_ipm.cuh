@@ -75,8 +75,9 @@ template <typename T, int N> struct Layout {
     static constexpr int HDR = KFF + N * 4;
     // Riccati / rollout scratch
     static constexpr int PN = HDR + N * HDR_S;   // 13x13 cost-to-go
-    static constexpr int FD = PN + 169;          // 9x13 dense dynamics Jacobian wrt (u, x)
-    static constexpr int PF = FD + 117;          // 13x13 = PN(:, x) * FD
+    static constexpr int FDS = 14;               // row stride of the dense 9x13 dynamics Jacobian wrt (u, x)
+    static constexpr int FD = PN + 169;
+    static constexpr int PF = FD + 9 * FDS;          // 13x13 = PN(:, x) * FD
     static constexpr int GG = PF + 169;          // 13x13 = FD' * PF(x, :)
     static constexpr int TV = GG + 169;          // 13    = p+ + PN d
     static constexpr int FT = TV + 13;           // 13    = FD' TV(x)
@@ -167,45 +168,57 @@ __device__ __forceinline__ void tma_store(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// in-register Cholesky of a 4x4 SPD matrix given row-major a[16]; L (lower, 10 values) returned
-// as l[10] = {l00, l10,l11, l20,l21,l22, l30,l31,l32,l33}; returns false on a non-positive pivot.
-template <typename T> __device__ __forceinline__ bool chol4(const T* a, T l[10])
+// in-register Cholesky of a 4x4 SPD matrix given row-major a[16] (lower triangle used); L (10 values)
+// as l[10] = {l00, l10,l11, l20,l21,l22, l30,l31,l32,l33}, li[4] = 1/diag (no divisions anywhere:
+// 1/sqrt(d) comes from rsqrt); returns false on a non-positive pivot.
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+template <typename T> __device__ __forceinline__ bool chol4(const T* a, T l[10], T li[4])
 {
     bool ok = true;
     T d = a[0];
     ok &= d > T(0);
-    l[0] = sqrt_t(d);
-    T i0 = T(1) / l[0];
-    l[1] = a[4] * i0; l[3] = a[8] * i0; l[6] = a[12] * i0;
+    li[0] = rsqrt_t(d); l[0] = d * li[0];
+    l[1] = a[4] * li[0]; l[3] = a[8] * li[0]; l[6] = a[12] * li[0];
     d = a[5] - l[1] * l[1];
     ok &= d > T(0);
-    l[2] = sqrt_t(d);
-    T i1 = T(1) / l[2];
-    l[4] = (a[9] - l[3] * l[1]) * i1;
-    l[7] = (a[13] - l[6] * l[1]) * i1;
+    li[1] = rsqrt_t(d); l[2] = d * li[1];
+    l[4] = (a[9] - l[3] * l[1]) * li[1];
+    l[7] = (a[13] - l[6] * l[1]) * li[1];
     d = a[10] - l[3] * l[3] - l[4] * l[4];
     ok &= d > T(0);
-    l[5] = sqrt_t(d);
-    T i2 = T(1) / l[5];
-    l[8] = (a[14] - l[6] * l[3] - l[7] * l[4]) * i2;
+    li[2] = rsqrt_t(d); l[5] = d * li[2];
+    l[8] = (a[14] - l[6] * l[3] - l[7] * l[4]) * li[2];
     d = a[15] - l[6] * l[6] - l[7] * l[7] - l[8] * l[8];
     ok &= d > T(0);
-    l[9] = sqrt_t(d);
+    li[3] = rsqrt_t(d); l[9] = d * li[3];
     return ok;
 }
-template <typename T> __device__ __forceinline__ void fsub4(const T l[10], T x[4])
+template <typename T> __device__ __forceinline__ void fsub4(const T l[10], const T li[4], T x[4])
 {
-    x[0] = x[0] / l[0];
-    x[1] = (x[1] - l[1] * x[0]) / l[2];
-    x[2] = (x[2] - l[3] * x[0] - l[4] * x[1]) / l[5];
-    x[3] = (x[3] - l[6] * x[0] - l[7] * x[1] - l[8] * x[2]) / l[9];
+    x[0] = x[0] * li[0];
+    x[1] = (x[1] - l[1] * x[0]) * li[1];
+    x[2] = (x[2] - l[3] * x[0] - l[4] * x[1]) * li[2];
+    x[3] = (x[3] - l[6] * x[0] - l[7] * x[1] - l[8] * x[2]) * li[3];
 }
-template <typename T> __device__ __forceinline__ void bsub4(const T l[10], T x[4])
+template <typename T> __device__ __forceinline__ void bsub4(const T l[10], const T li[4], T x[4])
 {
-    x[3] = x[3] / l[9];
-    x[2] = (x[2] - l[8] * x[3]) / l[5];
-    x[1] = (x[1] - l[4] * x[2] - l[7] * x[3]) / l[2];
-    x[0] = (x[0] - l[1] * x[1] - l[3] * x[2] - l[6] * x[3]) / l[0];
+    x[3] = x[3] * li[3];
+    x[2] = (x[2] - l[8] * x[3]) * li[2];
+    x[1] = (x[1] - l[4] * x[2] - l[7] * x[3]) * li[1];
+    x[0] = (x[0] - l[1] * x[1] - l[3] * x[2] - l[6] * x[3]) * li[0];
+}
+// dot product of n (compile-time) strided shared-memory operands in three independent chains
+template <typename T, int n, int sa, int sb> __device__ __forceinline__ T dot3(const T* a, const T* b, T init)
+{
+    T c0 = init, c1 = T(0), c2 = T(0);
+#pragma unroll
+    for (int q = 0; q < n; q += 3) {
+        c0 += a[q * sa] * b[q * sb];
+        if (q + 1 < n) c1 += a[(q + 1) * sa] * b[(q + 1) * sb];
+        if (q + 2 < n) c2 += a[(q + 2) * sa] * b[(q + 2) * sb];
+    }
+    return (c0 + c1) + c2;
 }
 
 // =====================================================================================
@@ -373,132 +386,166 @@ template <typename T, int N> struct Solver {
     }
 
     // ------------------------------------------------------------- Riccati backward -----
+    // Four warp-synchronous phases per stage.  Every lane owns a fixed set of matrix entries
+    // (compile-time trip counts, per-lane offsets hoisted out of the stage loop), the dense 9x13
+    // Jacobian F is refreshed by a table-driven copy of its 51 variable entries (the 0 / 1 / h
+    // pattern is written once), and all dot products run as three independent FMA chains.
+    //   A: PF = P+(:,x) F,  tv = p+ + P+ d           B: Q blocks (F' PF + coupling), q~ vectors
+    //   C: 4x4 Cholesky (rsqrt, no divisions), Y = L^-1 [Q_ux Q_uq | q_u], K = -L^-T Y
+    //   D: P_k = blkdiag(Q_xx, Phi_qq) - Y'Y, p_k = q_xi - Y' y0, F <- stage k-1
     // Returns false on a non-positive pivot.
+    __device__ __forceinline__ static int fd_slot(int c)
+    {   // compact Jacobian word c -> offset in the dense F (v-ordering columns: w0 w1 w2 T p0..2 v0..2 r0..2)
+        constexpr int S = L::FDS;
+        if (c < JPR) return (c / 3) * S + 7 + c % 3;                    // d pos+/d vel
+        if (c < JPT) return ((c - JPR) / 3) * S + 10 + (c - JPR) % 3;   // d pos+/d rpy
+        if (c < JVV) return (c - JPT) * S + 3;                          // d pos+/d T
+        if (c < JVR) return (3 + (c - JVV) / 3) * S + 7 + (c - JVV) % 3;
+        if (c < JVT) return (3 + (c - JVR) / 3) * S + 10 + (c - JVR) % 3;
+        if (c < JVW) return (3 + c - JVT) * S + 3;
+        return (3 + (c - JVW) / 3) * S + (c - JVW) % 3;                 // d vel+/d rates
+    }
+
     __device__ bool riccati_backward()
     {
+        constexpr int FDS = L::FDS;
         T* PN = sm + L::PN; T* FD = sm + L::FD; T* PF = sm + L::PF; T* GG = sm + L::GG;
-        T* TV = sm + L::TV; T* FT = sm + L::FT; T* QUU = sm + L::QUU; T* QUR = sm + L::QUR;
+        T* TV = sm + L::TV; T* QUU = sm + L::QUU; T* QUR = sm + L::QUR;
         T* QV = sm + L::QV; T* QXI = sm + L::QXI; T* YS = sm + L::YS; T* Y0 = sm + L::Y0;
         bool ok = true;
-        // lower-triangle entries (i >= j) of a 13x13 handled by this lane: e = lane, lane+32, lane+64
-        int ti[3], tj[3];
+        // lower-triangle entries (i >= j) of a 13x13 owned by this lane: e = lane, lane+32, lane+64 (< 91)
+        int ti[3], tj[3], goff[3], poff[3];
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const int e = lane + 32 * t;
             int i = 0;
             while ((i + 1) * (i + 2) / 2 <= e) i++;
-            ti[t] = i;
-            tj[t] = e - i * (i + 1) / 2;
+            const int j = e - i * (i + 1) / 2;
+            ti[t] = i; tj[t] = j;
+            // phase D (xi-ordering): where the additive terms of P_k[i][j] live (-1: none)
+            goff[t] = (i < 9) ? (4 + i) * 13 + 4 + j : -1;                                   // Q_xx part in GG
+            poff[t] = (i < 9) ? (i == j ? 8 + i : (i < 3 ? 17 + i + j - 1 : -1))             // Phi_xx
+                              : (i == j ? 4 + i - 9 : -1);                                   // Phi_qq
         }
+        const int fdd0 = fd_slot(lane), fdd1 = fd_slot(lane + 32 < NJC ? lane + 32 : NJC - 1);
+        const bool has1 = lane + 32 < NJC;
+        // constant pattern of F (written once per sweep): zeros, identities, h
+        for (int e = lane; e < 9 * FDS; e += 32) FD[e] = T(0);
+        __syncwarp();
+        if (lane < 3) {
+            FD[lane * FDS + 4 + lane] = T(1);
+            FD[(6 + lane) * FDS + 10 + lane] = T(1);
+            FD[(6 + lane) * FDS + lane] = C::h;
+        }
+        {
+            const T* jcn = JC + (N - 2) * NJC;
+            FD[fdd0] = jcn[lane];
+            if (has1) FD[fdd1] = jcn[lane + 32];
+        }
+        __syncwarp();
         for (int k = N - 1; k >= 0; k--) {
             const bool nx = (k < N - 1);
             const T* phi = PHID + k * L::PHI_S;
             const T* gk = G + k * NZ;
             if (nx) {
-                // S1: dense F and tv = p+ + P+ d
-                const T* jc = JC + k * NJC;
-                for (int e = lane; e < 117; e += 32) FD[e] = f_dense<T>(jc, e / 13, e % 13);
-                if (lane < NXI) {
-                    T acc = P[(k + 1) * NXI + lane];
+                // ---- phase A ------------------------------------------------------------------
+                const T* dk = D + k * NXI;
 #pragma unroll
-                    for (int j = 0; j < NXI; j++) acc += PN[lane * 13 + j] * D[k * NXI + j];
-                    TV[lane] = acc;
+                for (int t = 0; t < 6; t++) {
+                    const int e = lane + 32 * t;
+                    if (e < 169) {
+                        const int i = e / 13, j = e - 13 * i;
+                        PF[e] = dot3<T, 9, 1, FDS>(PN + i * 13, FD + j, T(0));
+                    } else if (e < 182) {
+                        const int i = e - 169;
+                        TV[i] = dot3<T, 13, 1, 1>(PN + i * 13, dk, P[(k + 1) * NXI + i]);
+                    }
                 }
                 __syncwarp();
-                // S2: PF = PN(:, 0:9) * FD  (13x13),  ft = FD' tv(0:9)
-                for (int e = lane; e < 169; e += 32) {
-                    const int i = e / 13, j = e - 13 * i;
-                    T acc = T(0);
+                // ---- phase B ------------------------------------------------------------------
 #pragma unroll
-                    for (int q = 0; q < 9; q++) acc += PN[i * 13 + q] * FD[q * 13 + j];
-                    PF[e] = acc;
+                for (int t = 0; t < 4; t++) {
+                    const int e = lane + 32 * t;
+                    if (t < 3 && e < 91) {
+                        const int i = ti[t], j = tj[t];            // v-ordering (u0..3, x0..8), i >= j
+                        T acc = dot3<T, 9, FDS, 13>(FD + i, PF + j, T(0));
+                        if (i < 4) {                               // Q_uu (then j < 4 too)
+                            acc += PN[(9 + i) * 13 + 9 + j] + PF[(9 + i) * 13 + j] + PF[(9 + j) * 13 + i];
+                            if (i == j) acc += phi[i];
+                            QUU[i * 4 + j] = acc;
+                            QUU[j * 4 + i] = acc;
+                        } else if (j < 4) {                        // Q_ux[a = j][x = i - 4]
+                            QUR[j * 13 + i - 4] = acc + PF[(9 + j) * 13 + i];
+                        } else {
+                            GG[i * 13 + j] = acc;                  // Q_xx (lower), consumed in phase D
+                        }
+                    } else if (e >= 91 && e < 108) {               // q~: w < 4 -> q_u, else q_xi
+                        const int w = e - 91;
+                        T v;
+                        if (w < 13) {
+                            const T base = (w < 4) ? gk[w] + TV[9 + w] : gk[w + 4];
+                            v = dot3<T, 9, FDS, 1>(FD + w, TV, base);
+                        } else {
+                            v = gk[w - 9];
+                        }
+                        if (w < 4) QV[w] = v; else QXI[w - 4] = v;
+                    }
                 }
-                if (lane < 13) {
-                    T acc = T(0);
-#pragma unroll
-                    for (int q = 0; q < 9; q++) acc += FD[q * 13 + lane] * TV[q];
-                    FT[lane] = acc;
+                if (lane < 16) QUR[(lane >> 2) * 13 + 9 + (lane & 3)] = ((lane >> 2) == (lane & 3)) ? phi[20] : T(0);
+            } else {
+                // terminal stage: no dynamics behind it
+                if (lane < 16) {
+                    QUU[lane] = ((lane >> 2) == (lane & 3)) ? phi[lane >> 2] : T(0);
+                    QUR[(lane >> 2) * 13 + 9 + (lane & 3)] = ((lane >> 2) == (lane & 3)) ? phi[20] : T(0);
                 }
-                __syncwarp();
-                // S3: GG = FD' * PF(0:9, :)  (symmetric 13x13; lower triangle, mirrored)
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if (lane + 32 * t >= 91) break;
-                    const int i = ti[t], j = tj[t];
-                    T acc = T(0);
-#pragma unroll
-                    for (int q = 0; q < 9; q++) acc += FD[q * 13 + i] * PF[q * 13 + j];
-                    GG[i * 13 + j] = acc;
-                    GG[j * 13 + i] = acc;
-                }
-                __syncwarp();
-            }
-            // S4: Q blocks.  v-ordering of FD columns: (u0..u3, x0..x8); xi-ordering: (x0..x8, q0..q3)
-            const T wr2 = phi[20];
-            for (int e = lane; e < 85; e += 32) {
-                if (e < 16) {
-                    const int a = e >> 2, b = e & 3;
-                    T v = (a == b) ? phi[a] : T(0);
-                    if (nx) v += GG[a * 13 + b] + PN[(9 + a) * 13 + 9 + b] + PF[(9 + a) * 13 + b] + PF[(9 + b) * 13 + a];
-                    QUU[e] = v;
-                } else if (e < 68) {
-                    const int a = (e - 16) / 13, j = (e - 16) - 13 * a;
-                    T v;
-                    if (j < 9) v = nx ? GG[a * 13 + 4 + j] + PF[(9 + a) * 13 + 4 + j] : T(0);
-                    else v = (j - 9 == a) ? wr2 : T(0);
-                    QUR[a * 13 + j] = v;
-                } else if (e < 72) {
-                    const int a = e - 68;
-                    QV[a] = gk[a] + (nx ? TV[9 + a] + FT[a] : T(0));
-                } else {
-                    const int j = e - 72;
-                    QXI[j] = (j < 9) ? gk[8 + j] + (nx ? FT[4 + j] : T(0)) : gk[4 + j - 9];
-                }
+                for (int e = lane; e < 36; e += 32) QUR[(e / 9) * 13 + e % 9] = T(0);
+                if (lane < 4) QV[lane] = gk[lane];
+                if (lane < 13) QXI[lane] = (lane < 9) ? gk[8 + lane] : gk[lane - 5];
             }
             __syncwarp();
-            // S5: factor the 4x4 pivot block (redundantly, in registers), solve the 13+1 columns
-            T l[10];
-            ok &= chol4<T>(QUU, l);
+            // ---- phase C: factor the pivot block redundantly in registers, solve 13 + 1 columns ----
+            T l[10], li[4];
+            {
+                T a[16];
+                a[0] = QUU[0]; a[4] = QUU[4]; a[5] = QUU[5]; a[8] = QUU[8]; a[9] = QUU[9]; a[10] = QUU[10];
+                a[12] = QUU[12]; a[13] = QUU[13]; a[14] = QUU[14]; a[15] = QUU[15];
+                ok &= chol4<T>(a, l, li);
+            }
             if (lane < 14) {
                 T x[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) x[r] = (lane < 13) ? QUR[r * 13 + lane] : QV[r];
-                fsub4<T>(l, x);
-                if (lane < 13) {
+                fsub4<T>(l, li, x);
+                T* ys = (lane < 13) ? YS + lane : Y0;
+                const int ystr = (lane < 13) ? 13 : 1;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) YS[r * 13 + lane] = x[r];
-                } else {
+                for (int r = 0; r < 4; r++) ys[r * ystr] = x[r];
+                bsub4<T>(l, li, x);
+                T* kg = (lane < 13) ? KG + k * 52 + lane : KFF + k * 4;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) Y0[r] = x[r];
-                }
-                bsub4<T>(l, x);
-                if (lane < 13) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) KG[k * 52 + r * 13 + lane] = -x[r];
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) KFF[k * 4 + r] = -x[r];
-                }
+                for (int r = 0; r < 4; r++) kg[r * ystr] = -x[r];
             }
             __syncwarp();
-            // S6: cost-to-go  P_k = blkdiag(Q_xx, Phi_qq) - YS' YS ,  p_k = q_xi - YS' y0
+            // ---- phase D ------------------------------------------------------------------------
 #pragma unroll
-            for (int t = 0; t < 3; t++) {
-                if (lane + 32 * t >= 91) break;
-                const int i = ti[t], j = tj[t];
-                T v = T(0);
-                if (i < 9) v = phi_xx(phi, i, j) + (nx ? GG[(4 + i) * 13 + 4 + j] : T(0));
-                else if (i == j) v = phi[4 + i - 9];
-#pragma unroll
-                for (int r = 0; r < 4; r++) v -= YS[r * 13 + i] * YS[r * 13 + j];
-                PN[i * 13 + j] = v;
-                PN[j * 13 + i] = v;
+            for (int t = 0; t < 4; t++) {
+                const int e = lane + 32 * t;
+                if (t < 3 && e < 91) {
+                    const int i = ti[t], j = tj[t];                // xi-ordering (x0..8, q0..3), i >= j
+                    T v = (nx && goff[t] >= 0) ? GG[goff[t]] : T(0);
+                    if (poff[t] >= 0) v += phi[poff[t]];
+                    v -= (YS[i] * YS[j] + YS[13 + i] * YS[13 + j]) + (YS[26 + i] * YS[26 + j] + YS[39 + i] * YS[39 + j]);
+                    PN[i * 13 + j] = v;
+                    PN[j * 13 + i] = v;
+                } else if (e >= 91 && e < 104) {
+                    const int i = e - 91;
+                    P[k * NXI + i] = QXI[i] - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
+                }
             }
-            if (lane < 13) {
-                T v = QXI[lane];
-#pragma unroll
-                for (int r = 0; r < 4; r++) v -= YS[r * 13 + lane] * Y0[r];
-                P[k * NXI + lane] = v;
+            if (k >= 1 && k <= N - 2) {                            // F of the next stage to be processed (k - 1)
+                const T* jcn = JC + (k - 1) * NJC;
+                FD[fdd0] = jcn[lane];
+                if (has1) FD[fdd1] = jcn[lane + 32];
             }
             __syncwarp();
             if (fac_out) {   // factor block of stage k: [P_k packed lower 91 | K_k 52 | Quu^-1 packed lower 10 | J_k 51]
@@ -508,11 +555,11 @@ template <typename T, int N> struct Solver {
                     if (lane + 32 * t < 91) fk[lane + 32 * t] = PN[ti[t] * 13 + tj[t]];
                 for (int e = lane; e < 52; e += 32) fk[91 + e] = KG[k * 52 + e];
                 if (lane < 4) {   // column `lane` of Quu^-1 via the Cholesky factor
-                    T x[4] = {T(0), T(0), T(0), T(0)};
+                    T x[4];
 #pragma unroll
                     for (int r = 0; r < 4; r++) x[r] = (r == lane) ? T(1) : T(0);
-                    fsub4<T>(l, x);
-                    bsub4<T>(l, x);
+                    fsub4<T>(l, li, x);
+                    bsub4<T>(l, li, x);
 #pragma unroll
                     for (int r = 0; r < 4; r++)
                         if (r >= lane) fk[143 + r * (r + 1) / 2 + lane] = x[r];
@@ -524,52 +571,61 @@ template <typename T, int N> struct Solver {
     }
 
     // ------------------------------------------------------------- forward rollout ------
+    // dz_k = (du, dq, dx): du = K dxi + kff (8 lanes per row + shuffles); dxi+ = [F (du, dx) + d_x ; du + d_q]
+    // with the rows of F addressed through per-lane offsets into the compact Jacobian (branch-free).
     __device__ bool rollout()
     {
         T* PN = sm + L::PN; T* DXI = sm + L::DXI;
         bool ok = true;
-        // stage 0: x fixed (dx = 0), u_prev free: dq = -Pqq^-1 p_q
-        {
-            T a[16], l[10], x[4];
+        {   // stage 0: x fixed (dx = 0), u_prev free: dq = -Pqq^-1 p_q
+            T a[16], l[10], li[4], x[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) a[4 * r + c] = PN[(9 + r) * 13 + 9 + c];
+                for (int c = 0; c <= r; c++) a[4 * r + c] = PN[(9 + r) * 13 + 9 + c];
                 x[r] = -P[9 + r];
             }
-            ok = chol4<T>(a, l);
-            fsub4<T>(l, x);
-            bsub4<T>(l, x);
-            if (lane < 13) DXI[lane] = (lane < 9) ? T(0) : x[lane - 9];
+            ok = chol4<T>(a, l, li);
+            fsub4<T>(l, li, x);
+            bsub4<T>(l, li, x);
+            if (lane < 13) DXI[lane] = (lane < 9) ? T(0) : (lane == 9 ? x[0] : (lane == 10 ? x[1] : (lane == 11 ? x[2] : x[3])));
         }
+        // per-lane row description of dxi+ (lane = row in xi-ordering)
+        const int rt = lane < 3 ? 0 : (lane < 6 ? 1 : (lane < 9 ? 2 : (lane < 13 ? 3 : 4)));   // pos+, vel+, rpy+, q+, idle
+        const int rr = lane < 3 ? lane : (lane < 6 ? lane - 3 : 0);
+        const int offT = rt == 0 ? JPT + rr : (rt == 1 ? JVT + rr : 0);
+        const int offV = rt == 0 ? JPV + 3 * rr : (rt == 1 ? JVV + 3 * rr : 0);
+        const int offR = rt == 0 ? JPR + 3 * rr : (rt == 1 ? JVR + 3 * rr : 0);
+        const int offW = rt == 1 ? JVW + 3 * rr : 0;
+        const T mMain = rt <= 1 ? T(1) : T(0), mW = rt == 1 ? T(1) : T(0);
+        const T mSelf = (rt == 0 || rt == 2) ? T(1) : T(0);
+        const T cDu = rt == 2 ? C::h : (rt == 3 ? T(1) : T(0));
+        const int duSrc = 8 * ((rt == 2 ? lane - 6 : lane - 9) & 3);
+        const int lrow = lane < 13 ? lane : 0;
+        const int r4 = lane >> 3, part = lane & 7;
         __syncwarp();
         for (int k = 0; k < N; k++) {
-            // du_r = kff_r + K[r][:] . dxi   (8 lanes per row, shuffle-reduced)
-            const int r = lane >> 3, part = lane & 7;
-            T acc = T(0);
-            for (int i = part; i < 13; i += 8) acc += KG[k * 52 + r * 13 + i] * DXI[i];
+            const T* kg = KG + k * 52 + r4 * 13;
+            T acc = kg[part] * DXI[part];
+            if (part < 5) acc += kg[part + 8] * DXI[part + 8];
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += KFF[k * 4 + r];
-            T v[13];   // (du(4), dx(9))
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = __shfl_sync(0xffffffffu, acc, 8 * q);
-#pragma unroll
-            for (int q = 0; q < 9; q++) v[4 + q] = DXI[q];
-            const T du_l = __shfl_sync(0xffffffffu, acc, 8 * (lane & 3));        // du[lane & 3]
-            const T du_q = __shfl_sync(0xffffffffu, acc, 8 * ((lane - 9) & 3));  // du[lane - 9] for lanes 9..12
+            acc += KFF[k * 4 + r4];
+            const T dw0 = __shfl_sync(0xffffffffu, acc, 0), dw1 = __shfl_sync(0xffffffffu, acc, 8);
+            const T dw2 = __shfl_sync(0xffffffffu, acc, 16), dT = __shfl_sync(0xffffffffu, acc, 24);
+            const T du_l = __shfl_sync(0xffffffffu, acc, 8 * (lane & 3));   // du[lane & 3]
+            const T du_s = __shfl_sync(0xffffffffu, acc, duSrc);            // du feeding row `lane` of dxi+
+            const T self = DXI[lrow];
             if (lane < NZ) DZ[k * NZ + lane] = (lane < 4) ? du_l : (lane < 8 ? DXI[5 + lane] : DXI[lane - 8]);
             T nxt = T(0);
-            if (k < N - 1 && lane < 13) {
-                if (lane < 9) {
-                    const T* jc = JC + k * NJC;
-                    nxt = D[k * NXI + lane];
-#pragma unroll
-                    for (int c = 0; c < 13; c++) nxt += f_dense<T>(jc, lane, c) * v[c];
-                } else {
-                    nxt = du_q + D[k * NXI + lane];
-                }
+            if (k < N - 1) {
+                const T* jc = JC + k * NJC;
+                const T m0 = jc[offT] * dT + jc[offV] * DXI[3] + jc[offR] * DXI[6];
+                const T m1 = jc[offV + 1] * DXI[4] + jc[offR + 1] * DXI[7];
+                const T m2 = jc[offV + 2] * DXI[5] + jc[offR + 2] * DXI[8];
+                const T mw = jc[offW] * dw0 + jc[offW + 1] * dw1 + jc[offW + 2] * dw2;
+                nxt = D[k * NXI + lrow] + mSelf * self + cDu * du_s + mMain * ((m0 + m1) + m2) + mW * mw;
             }
             __syncwarp();
             if (k < N - 1 && lane < 13) DXI[lane] = nxt;
@@ -579,26 +635,32 @@ template <typename T, int N> struct Solver {
     }
 
     // ------------------------------------ costates of the QP (new equality multipliers) ---
-    // y_k = [Phi_k dz_k + g~_k + J_k' y_{k+1}]_xi , stored over p_k (c-ordering [x; q]).
+    // y_k = [Phi_k dz_k + g~_k + J_k' y_{k+1}]_xi , stored over p_k (c-ordering [x; q]); the column of
+    // J' each lane needs is addressed through per-lane offsets into the compact Jacobian.
     __device__ void costates()
     {
+        const int i = lane < 13 ? lane : 0;                       // xi index handled by this lane
+        const int zi = e_col(i);                                   // its z index
+        const int ct = i < 3 ? 0 : (i < 6 ? 1 : (i < 9 ? 2 : 3));  // pos, vel, rpy, q
+        const int jj = ct == 1 ? i - 3 : (ct == 2 ? i - 6 : 0);
+        const int offP = ct == 1 ? JPV + jj : (ct == 2 ? JPR + jj : 0);    // column jj of d pos+/d(.)
+        const int offV = ct == 1 ? JVV + jj : (ct == 2 ? JVR + jj : 0);    // column jj of d vel+/d(.)
+        const T mJ = (ct == 1 || ct == 2) ? T(1) : T(0), mSelf = (ct == 0 || ct == 2) ? T(1) : T(0);
+        // off-diagonal position-block terms: (phi slot, dz index) pairs
+        const int pa = i == 2 ? 18 : 17, da = i == 0 ? 9 : 8, pb = i == 0 ? 18 : 19, db = i == 2 ? 9 : 10;
+        const T mP = ct == 0 ? T(1) : T(0), mQ = ct == 3 ? T(1) : T(0);
+        const int cq = ct == 3 ? i - 9 : 0;
         for (int k = N - 1; k >= 1; k--) {
-            T v = T(0);
-            if (lane < 13) {
-                const T* phi = PHID + k * L::PHI_S;
-                const T* dz = DZ + k * NZ;
-                if (lane < 9) {
-                    v = G[k * NZ + 8 + lane] + phi[8 + lane] * dz[8 + lane];
-                    if (lane < 3) {
-#pragma unroll
-                        for (int j = 0; j < 3; j++)
-                            if (j != lane) v += phi_xx(phi, lane, j) * dz[8 + j];
-                    }
-                    if (k < N - 1) v += jt_y<T>(JC + k * NJC, P + (k + 1) * NXI, 8 + lane);
-                } else {
-                    const int c = lane - 9;
-                    v = G[k * NZ + 4 + c] + phi[4 + c] * dz[4 + c] + phi[20] * dz[c];
-                }
+            const T* phi = PHID + k * L::PHI_S;
+            const T* dz = DZ + k * NZ;
+            T v = G[k * NZ + zi] + phi[zi] * dz[zi] + mP * (phi[pa] * dz[da] + phi[pb] * dz[db]) + mQ * phi[20] * dz[cq];
+            if (k < N - 1) {
+                const T* jc = JC + k * NJC;
+                const T* yn = P + (k + 1) * NXI;
+                const T s0 = jc[offP] * yn[0] + jc[offV] * yn[3];
+                const T s1 = jc[offP + 3] * yn[1] + jc[offV + 3] * yn[4];
+                const T s2 = jc[offP + 6] * yn[2] + jc[offV + 6] * yn[5];
+                v += mJ * ((s0 + s1) + s2) + mSelf * yn[i];
             }
             __syncwarp();
             if (lane < 13) P[k * NXI + lane] = v;
