@@ -88,7 +88,8 @@ template <typename T, int N> struct Layout {
     static constexpr int YS = QXI + 13;          // 4x13  L^-1 QUR
     static constexpr int Y0 = YS + 52;           // 4     L^-1 QV
     static constexpr int DXI = Y0 + 4;           // 13
-    static constexpr int FIXED_END = DXI + 13 + 2;
+    static constexpr int BND = DXI + 14;         // lb(17) | ub(17)
+    static constexpr int FIXED_END = BND + 2 * NZ;
     // mcap-dependent tail: ROWS [N][4*mcap+1], S [N][mcap|1], LC [N][mcap|1]
     __host__ __device__ static constexpr int row_stride(int mcap) { return 4 * mcap + 1; }
     __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
@@ -126,8 +127,8 @@ template <typename T> __device__ __forceinline__ T warp_min(T v)
     return v;
 }
 template <typename T> struct Eps;
-template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int loggrp = 8; };
-template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f; static constexpr int loggrp = 3; };
+template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int logvars = 4, logrows = 8; };
+template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f; static constexpr int logvars = 1, logrows = 2; };
 
 __device__ __forceinline__ int e_col(int i) { return i < 9 ? 8 + i : i - 5; }   // xi index -> z index
 __device__ __forceinline__ bool is_free(int k, int i) { return k > 0 || i < 8; }
@@ -231,60 +232,59 @@ template <typename T, int N> struct Solver {
     int* nr;      // live rows per stage
     int lane, mcap, RS, SS;
     bool final_variant;
-    T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *ROWS, *S, *LC;
+    T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *ROWS, *S, *LC, *BND;
     T* fac_out = nullptr;   // when set, riccati_backward streams the factor (P | K | Quu^-1 | J) to HBM
 
     __device__ __forceinline__ int live(int k) const { return k == 0 ? 0 : min(nr[k], mcap); }
 
     // ---------------------------------------------------------------- model evaluation ---
-    // FULL: at z, storing gradient / compact Jacobian / defects.  !FULL: at z + a dz (values only).
-    template <bool FULL> __device__ void evaluate(T a, T& f_out, T& th_out, T& ls_out)
+    // At z + a dz ("lanes = stages"): cost, gradient, compact Jacobian, defects, theta and the barrier
+    // log-sum.  One code path serves the initial point (a = 0) and every line-search trial; an
+    // accepted trial's gradient / Jacobians / defects are exactly what the next iteration needs,
+    // so nothing is evaluated twice.  Logs are taken of fixed-size products (5 + ceil(m/8) logs per
+    // stage instead of 34 + m).
+    __device__ void evaluate(T a, T& f_out, T& th_out, T& ls_out)
     {
-        T f = T(0), th = T(0), ls = T(0), prod = T(1);
-        int np = 0;
-        auto acc_log = [&](T v) {
-            prod *= v;
-            if (++np == Eps<T>::loggrp) { ls += log_t(prod); prod = T(1); np = 0; }
-        };
+        T f = T(0), th = T(0), ls = T(0);
         for (int k = lane; k < N; k += 32) {
             T zk[NZ];
 #pragma unroll
-            for (int i = 0; i < NZ; i++) zk[i] = FULL ? Z[k * NZ + i] : Z[k * NZ + i] + a * DZ[k * NZ + i];
+            for (int i = 0; i < NZ; i++) zk[i] = Z[k * NZ + i] + a * DZ[k * NZ + i];
             const T* hdr = HDR + k * L::HDR_S;
-            f += objective<T, FULL>(zk, hdr, k == 0, final_variant && k == N - 1, G + k * NZ);
+            f += objective<T, true>(zk, hdr, k == 0, final_variant && k == N - 1, G + k * NZ);
             if (k < N - 1) {
                 T c[NXI];
-                dynamics<T, FULL>(zk, hdr + 3, c, JC + k * NJC);
+                dynamics<T, true>(zk, hdr + 3, c, JC + k * NJC);
 #pragma unroll
                 for (int i = 0; i < NXI; i++) {
                     const int zi = (k + 1) * NZ + e_col(i);
-                    T zn = FULL ? Z[zi] : Z[zi] + a * DZ[zi];
-                    T d = c[i] - zn;
+                    const T d = c[i] - (Z[zi] + a * DZ[zi]);
                     th += fabs(d);
-                    if (FULL) D[k * NXI + i] = d;
+                    D[k * NXI + i] = d;
                 }
             }
+            T prod = T(1);
 #pragma unroll
-            for (int i = 0; i < NZ; i++)
-                if (is_free(k, i)) {
-                    acc_log(zk[i] - lower_bound<T>(i));
-                    acc_log(upper_bound<T>(i) - zk[i]);
-                }
+            for (int i = 0; i < NZ; i++) {
+                T sl = zk[i] - lower_bound<T>(i), su = upper_bound<T>(i) - zk[i];
+                if (i >= 8 && k == 0) { sl = T(1); su = T(1); }      // stage-0 states are fixed, not bounded
+                prod *= sl * su;
+                if (i % Eps<T>::logvars == Eps<T>::logvars - 1 || i == NZ - 1) { ls += log_t(prod); prod = T(1); }
+            }
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 const T* r = ROWS + k * RS + 4 * j;
                 T sj = S[k * SS + j];
                 T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                if (!FULL) {
-                    T adz = r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10];
-                    sj += a * (-rc - adz);
-                    rc *= (T(1) - a);
-                }
+                const T adz = r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10];
+                sj += a * (-rc - adz);                 // trial slack s + a ds
+                rc *= (T(1) - a);                      // the constraint is linear: residual shrinks by (1 - a)
                 th += fabs(rc);
-                acc_log(sj);
+                prod *= sj;
+                if ((j & (Eps<T>::logrows - 1)) == Eps<T>::logrows - 1) { ls += log_t(prod); prod = T(1); }
             }
+            ls += log_t(prod);
         }
-        ls += log_t(prod);
         f_out = warp_sum(f);
         th_out = warp_sum(th);
         ls_out = warp_sum(ls);
@@ -296,33 +296,30 @@ template <typename T, int N> struct Solver {
         T rs = T(0), req = T(0), rin = T(0), cmx = T(0), cs = T(0), cmn = T(1e30);
         for (int k = lane; k < N; k += 32) {
             const int m = live(k);
-            T yn[NXI], yk[NXI];
-#pragma unroll
-            for (int i = 0; i < NXI; i++) {
-                yn[i] = (k < N - 1) ? Y[(k + 1) * NXI + i] : T(0);
-                yk[i] = (k > 0) ? Y[k * NXI + i] : T(0);
-            }
-            T al[3] = {T(0), T(0), T(0)};
+            const T* yn = Y + (k + 1) * NXI;   // only dereferenced for k < N-1
+            const T* yk = Y + k * NXI;         // row 0 stays zero
+            const T* jc = JC + k * NJC;
+            T al0 = T(0), al1 = T(0), al2 = T(0);
             for (int j = 0; j < m; j++) {
                 const T* r = ROWS + k * RS + 4 * j;
-                T sj = S[k * SS + j], lj = LC[k * SS + j];
-                al[0] += r[0] * lj; al[1] += r[1] * lj; al[2] += r[2] * lj;
-                T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                T cc = sj * lj;
+                const T sj = S[k * SS + j], lj = LC[k * SS + j];
+                al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T cc = sj * lj;
                 cs += cc; cmx = fmax(cmx, cc); cmn = fmin(cmn, cc);
                 rin = fmax(rin, fmax(fabs(rc), rc - sj));
             }
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                if (!is_free(k, i)) continue;
-                T zi = Z[k * NZ + i], zl = ZL[k * NZ + i], zu = ZU[k * NZ + i];
+            const int nfree = (k == 0) ? 8 : NZ;
+#pragma unroll 1
+            for (int i = 0; i < nfree; i++) {
+                const T zi = Z[k * NZ + i], zl = ZL[k * NZ + i], zu = ZU[k * NZ + i];
                 T r = G[k * NZ + i] - zl + zu;
-                if (k < N - 1) r += jt_y<T>(JC + k * NJC, yn, i);
+                if (k < N - 1) r += jt_y<T>(jc, yn, i);
                 if (i >= 8) r -= yk[i - 8];
-                else if (i >= 4) r -= yk[9 + i - 4];
-                if (i >= 8 && i < 11) r += al[i - 8];
+                else if (i >= 4) r -= yk[5 + i];
+                if (i >= 8 && i < 11) r += (i == 8 ? al0 : (i == 9 ? al1 : al2));
                 rs = fmax(rs, fabs(r));
-                T cl = (zi - lower_bound<T>(i)) * zl, cu = (upper_bound<T>(i) - zi) * zu;
+                const T cl = (zi - BND[i]) * zl, cu = (BND[NZ + i] - zi) * zu;
                 cs += cl + cu;
                 cmx = fmax(cmx, fmax(cl, cu));
                 cmn = fmin(cmn, fmin(cl, cu));
@@ -332,44 +329,44 @@ template <typename T, int N> struct Solver {
                 for (int i = 0; i < NXI; i++) req = fmax(req, fabs(D[k * NXI + i]));
             }
         }
-        // NaN-propagating reductions: fmax drops NaNs, so carry a finite flag through the sum
         rs_n = warp_max(rs); req_n = warp_max(req); rin_n = warp_max(rin); rcomp = warp_max(cmx);
         csum = warp_sum(cs); cmin = warp_min(cmn);
     }
 
     // ------------------------------------------ barrier-augmented stage Hessian and rhs ---
+    // bounds: flat over the N*17 (stage, variable) pairs, all 32 lanes busy; corridor rows: per stage.
     __device__ void assemble(T mu_t)
     {
-        for (int k = lane; k < N; k += 32) {
-            const T* hdr = HDR + k * L::HDR_S;
-            const bool first = (k == 0), ft = final_variant && (k == N - 1);
+        for (int e = lane; e < N * NZ; e += 32) {
+            const int k = e / NZ, i = e - k * NZ;
             T* phi = PHID + k * L::PHI_S;
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                if (is_free(k, i)) {
-                    T zi = Z[k * NZ + i];
-                    T isl = T(1) / (zi - lower_bound<T>(i)), isu = T(1) / (upper_bound<T>(i) - zi);
-                    phi[i] = cost_hess_diag<T>(i, hdr, first, ft) + ZL[k * NZ + i] * isl + ZU[k * NZ + i] * isu;
-                    G[k * NZ + i] += mu_t * (isu - isl);
-                } else {
-                    phi[i] = T(1);
-                    G[k * NZ + i] = T(0);
-                }
+            if (e < 8 || e >= NZ) {
+                const T zi = Z[e];
+                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                phi[i] = cost_hess_diag<T>(i, HDR + k * L::HDR_S, k == 0, final_variant && k == N - 1) + ZL[e] * isl + ZU[e] * isu;
+                G[e] += mu_t * (isu - isl);
+            } else {
+                phi[i] = T(1);
+                G[e] = T(0);
             }
+        }
+        __syncwarp();
+        for (int k = lane; k < N; k += 32) {
+            T* phi = PHID + k * L::PHI_S;
             T o01 = T(0), o02 = T(0), o12 = T(0), d0 = T(0), d1 = T(0), d2 = T(0), g0 = T(0), g1 = T(0), g2 = T(0);
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 const T* r = ROWS + k * RS + 4 * j;
-                T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
-                T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                T sg = lj * is, tt = (mu_t + lj * rc) * is;
+                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T sg = lj * is, tt = (mu_t + lj * rc) * is;
                 d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
                 o01 += r[0] * r[1] * sg; o02 += r[0] * r[2] * sg; o12 += r[1] * r[2] * sg;
                 g0 += r[0] * tt; g1 += r[1] * tt; g2 += r[2] * tt;
             }
             phi[8] += d0; phi[9] += d1; phi[10] += d2;
             phi[17] = o01; phi[18] = o02; phi[19] = o12;
-            phi[20] = T(-2) * hdr[8];   // H[u_i][uprev_i]
+            phi[20] = T(-2) * HDR[k * L::HDR_S + 8];   // H[u_i][uprev_i]
             if (k > 0) { G[k * NZ + 8] += g0; G[k * NZ + 9] += g1; G[k * NZ + 10] += g2; }
         }
     }
@@ -669,67 +666,77 @@ template <typename T, int N> struct Solver {
     }
 
     // ------------------------------------------- multiplier steps, fraction to boundary ---
+    // The largest admissible steps are tau / max_i(ratio_i) with ratio_i = -d(slack)/slack resp.
+    // -d(mult)/mult.  The maxima are tracked as fractions (num, den > 0) and compared by
+    // cross-multiplication, so the whole phase needs two divisions instead of four per variable:
+    //   -dz_l/z_l = (z_l (s_l + dz) - mu_t) / (s_l z_l),   -dz_u/z_u = (z_u (s_u - dz) - mu_t) / (s_u z_u).
+    __device__ __forceinline__ static void frac_max(T& bn, T& bd, T n, T d)
+    {
+        if (n * bd > bn * d) { bn = n; bd = d; }
+    }
     __device__ void step_lengths(T mu_t, T tau, T& ap_out, T& ad_out)
     {
-        T ap = T(1), ad = T(1);
+        T pn = T(0), pd = T(1), dn = T(0), dd = T(1);
+        for (int e = lane; e < N * NZ; e += 32) {
+            if (!(e < 8 || e >= NZ)) continue;
+            const int i = e % NZ;
+            const T zi = Z[e], dzi = DZ[e], zl = ZL[e], zu = ZU[e];
+            const T sl = zi - BND[i], su = BND[NZ + i] - zi;
+            frac_max(pn, pd, -dzi, sl);
+            frac_max(pn, pd, dzi, su);
+            frac_max(dn, dd, zl * (sl + dzi) - mu_t, sl * zl);
+            frac_max(dn, dd, zu * (su - dzi) - mu_t, su * zu);
+        }
         for (int k = lane; k < N; k += 32) {
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                if (!is_free(k, i)) continue;
-                T zi = Z[k * NZ + i], dzi = DZ[k * NZ + i], zl = ZL[k * NZ + i], zu = ZU[k * NZ + i];
-                T sl = zi - lower_bound<T>(i), su = upper_bound<T>(i) - zi;
-                T dzl = (mu_t - zl * dzi) / sl - zl;
-                T dzu = (mu_t + zu * dzi) / su - zu;
-                if (dzi < T(0)) ap = fmin(ap, -tau * sl / dzi);
-                if (dzi > T(0)) ap = fmin(ap, tau * su / dzi);
-                if (dzl < T(0)) ad = fmin(ad, -tau * zl / dzl);
-                if (dzu < T(0)) ad = fmin(ad, -tau * zu / dzu);
-            }
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 const T* r = ROWS + k * RS + 4 * j;
-                T sj = S[k * SS + j], lj = LC[k * SS + j];
-                T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
-                T dl = (mu_t - lj * ds) / sj - lj;
-                if (ds < T(0)) ap = fmin(ap, -tau * sj / ds);
-                if (dl < T(0)) ad = fmin(ad, -tau * lj / dl);
+                const T sj = S[k * SS + j], lj = LC[k * SS + j];
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
+                frac_max(pn, pd, -ds, sj);
+                frac_max(dn, dd, lj * (sj + ds) - mu_t, sj * lj);
             }
         }
-        ap_out = warp_min(ap);
-        ad_out = warp_min(ad);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T n2 = __shfl_xor_sync(0xffffffffu, pn, o), d2 = __shfl_xor_sync(0xffffffffu, pd, o);
+            frac_max(pn, pd, n2, d2);
+            const T n3 = __shfl_xor_sync(0xffffffffu, dn, o), d3 = __shfl_xor_sync(0xffffffffu, dd, o);
+            frac_max(dn, dd, n3, d3);
+        }
+        ap_out = (pn > T(0)) ? fmin(T(1), tau * pd / pn) : T(1);
+        ad_out = (dn > T(0)) ? fmin(T(1), tau * dd / dn) : T(1);
     }
 
     // --------------------------------------------------------------- accept the step ----
     __device__ void update(T mu_t, T a, T ad)
     {
-        for (int k = lane; k < N; k += 32) {
+        for (int k = lane; k < N; k += 32) {               // corridor rows first: they read the old position
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 const T* r = ROWS + k * RS + 4 * j;
-                T sj = S[k * SS + j], lj = LC[k * SS + j];
-                T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
-                T dl = (mu_t - lj * ds) / sj - lj;
+                const T sj = S[k * SS + j], lj = LC[k * SS + j];
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
+                const T dl = (mu_t - lj * ds) / sj - lj;
                 S[k * SS + j] = sj + a * ds;
                 LC[k * SS + j] = lj + ad * dl;
             }
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                T zi = Z[k * NZ + i], dzi = DZ[k * NZ + i];
-                if (is_free(k, i)) {
-                    T zl = ZL[k * NZ + i], zu = ZU[k * NZ + i];
-                    T sl = zi - lower_bound<T>(i), su = upper_bound<T>(i) - zi;
-                    ZL[k * NZ + i] = zl + ad * ((mu_t - zl * dzi) / sl - zl);
-                    ZU[k * NZ + i] = zu + ad * ((mu_t + zu * dzi) / su - zu);
-                }
-                Z[k * NZ + i] = zi + a * dzi;
-            }
-            if (k >= 1) {
-#pragma unroll
-                for (int i = 0; i < NXI; i++) Y[k * NXI + i] += a * (P[k * NXI + i] - Y[k * NXI + i]);
-            }
         }
+        __syncwarp();
+        for (int e = lane; e < N * NZ; e += 32) {
+            const T zi = Z[e], dzi = DZ[e];
+            if (e < 8 || e >= NZ) {
+                const int i = e % NZ;
+                const T zl = ZL[e], zu = ZU[e];
+                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
+                ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
+            }
+            Z[e] = zi + a * dzi;
+        }
+        for (int e = NXI + lane; e < N * NXI; e += 32) Y[e] += a * (P[e] - Y[e]);
     }
 };
 
@@ -757,7 +764,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     s.final_variant = (prm.variant == 1);
     s.Z = sm + L::Z; s.DZ = sm + L::DZ; s.ZL = sm + L::ZL; s.ZU = sm + L::ZU; s.G = sm + L::G;
     s.Y = sm + L::Y; s.P = sm + L::P; s.D = sm + L::D; s.JC = sm + L::JC; s.PHID = sm + L::PHID;
-    s.KG = sm + L::KG; s.KFF = sm + L::KFF; s.HDR = sm + L::HDR;
+    s.KG = sm + L::KG; s.KFF = sm + L::KFF; s.HDR = sm + L::HDR; s.BND = sm + L::BND;
     s.ROWS = sm + L::rows_off(); s.S = sm + L::s_off(mcap); s.LC = sm + L::lc_off(mcap);
     const Opts& o = prm.o;
 
@@ -787,6 +794,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     __syncwarp();
 
     // ---- initial point -------------------------------------------------------------------
+    if (lane < NZ) { s.BND[lane] = lower_bound<T>(lane); s.BND[NZ + lane] = upper_bound<T>(lane); }
+    for (int e = lane; e < N * NZ; e += 32) s.DZ[e] = T(0);      // staging area is dead now; evaluate(0) reads 0 * dz
     int ncomp = 0;
     for (int k = lane; k < N; k += 32) {
 #pragma unroll
@@ -826,7 +835,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     int flag = 0, it = 0, nbt_total = 0;
     T alpha_p = T(0), alpha_d = T(0), rs_n = T(0), req_n = T(0), rin_n = T(0), rcomp = T(0), mu = T(0);
     T f_cur, th_cur, ls_cur;
-    s.template evaluate<true>(T(0), f_cur, th_cur, ls_cur);
+    s.evaluate(T(0), f_cur, th_cur, ls_cur);
     __syncwarp();
     for (it = 0;; it++) {
         T csum, cmin;
@@ -858,9 +867,10 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         const T th_noise = fmax(T(10) * Eps<T>::v * T(N * NXI) * T(20), T(0.01) * (T)o.tol_eq);
         T a = ap;
         int nbt = 0;
+        T ft, tht, lst;
         for (;;) {
-            T ft, tht, lst;
-            s.template evaluate<false>(a, ft, tht, lst);
+            s.evaluate(a, ft, tht, lst);
+            __syncwarp();
             const T pht = ft - mu_t * lst;
             const bool acc = (tht <= fmax((T(1) - T(1e-5)) * th_cur, th_noise)) ||
                              (pht <= ph0 - T(1e-5) * th_cur + T(10) * Eps<T>::v * fabs(ph0));
@@ -870,9 +880,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         }
         nbt_total += nbt;
         alpha_p = a; alpha_d = ad;
-        s.update(mu_t, a, ad);
-        __syncwarp();
-        s.template evaluate<true>(T(0), f_cur, th_cur, ls_cur);
+        s.update(mu_t, a, ad);     // gradient / Jacobians / defects of the accepted trial stay in place
+        f_cur = ft; th_cur = tht; ls_cur = lst;
         __syncwarp();
     }
 
