@@ -78,9 +78,8 @@ template <typename T, int N> struct BsLayout {
     static constexpr int FAC = 0;
     static constexpr int GZ = FAC + N * FAC_WORDS;   // g on entry, dz on exit
     static constexpr int DD = GZ + N * NZ;
-    static constexpr int WY = DD + N * NXI;          // P+ d (hoisted) on the way back, y on exit
-    static constexpr int PV = WY + N * NXI;          // p_k
-    static constexpr int KF = PV + N * NXI;          // feed-forward terms
+    static constexpr int WY = DD + N * NXI;          // P+ d (hoisted) -> p_k (backward) -> y (exit), all in place
+    static constexpr int KF = WY + N * NXI;          // feed-forward terms
     static constexpr int TV = KF + N * 4;            // 13 + pad
     static constexpr int DXI = TV + 16;
     static constexpr int TOTAL = DXI + 16;
@@ -91,17 +90,33 @@ template <typename T, int N> struct BsLayout {
 
 __device__ __forceinline__ int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
+// y_i = sum_j P[i][j] x[j] for a packed-lower symmetric 13x13: unrolled over j with compile-time
+// triangular offsets, one compare/select per term, three independent chains.
+template <typename T> __device__ __forceinline__ T sym13_row_dot(const T* Pk, int i, const T* x, T init)
+{
+    const int rowbase = i * (i + 1) / 2;
+    T c0 = init, c1 = T(0), c2 = T(0);
+#pragma unroll
+    for (int j = 0; j < NXI; j++) {
+        const int off = (j <= i) ? rowbase + j : j * (j + 1) / 2 + i;
+        const T t = Pk[off] * x[j];
+        if (j % 3 == 0) c0 += t; else if (j % 3 == 1) c1 += t; else c2 += t;
+    }
+    return (c0 + c1) + c2;
+}
+
 template <typename T, int N>
 __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams<T> prm)
 {
     using L = BsLayout<T, N>;
+    using C = Const<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x, b = blockIdx.x;
     if (b >= prm.B) return;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     T* sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
     T* FAC = sm + L::FAC; T* GZ = sm + L::GZ; T* DD = sm + L::DD; T* WY = sm + L::WY;
-    T* PV = sm + L::PV; T* KF = sm + L::KF; T* TV = sm + L::TV; T* DXI = sm + L::DXI;
+    T* KF = sm + L::KF; T* TV = sm + L::TV; T* DXI = sm + L::DXI;
 
     constexpr uint32_t bytes_f = N * FAC_WORDS * sizeof(T), bytes_g = N * NZ * sizeof(T), bytes_d = N * NXI * sizeof(T);
     if (lane == 0) {
@@ -111,108 +126,126 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
         tma_load(GZ, prm.g + (size_t)b * N * NZ, bytes_g, bar);
         tma_load(DD, prm.d + (size_t)b * N * NXI, bytes_d, bar);
     }
+    // ---- per-lane tables (overlap with the copy) ---------------------------------------------------
+    // backward: lane = z index zi of q~ = g + J' tv ;  J' tv = mA sum_r jc[oA + sA r] tv[r] + mB sum_r jc[oB + sB r] tv[3+r]
+    //           + c1 tv[i1] + c2 tv[i2]
+    const int zi = lane < NZ ? lane : 0;
+    const int zt = zi < 3 ? 0 : (zi == 3 ? 1 : (zi < 8 ? 2 : (zi < 11 ? 3 : (zi < 14 ? 4 : 5))));   // rate, T, uprev, pos, vel, rpy
+    const int zj = zt == 0 ? zi : (zt == 3 ? zi - 8 : (zt == 4 ? zi - 11 : (zt == 5 ? zi - 14 : 0)));
+    const int oA = zt == 1 ? JPT : (zt == 4 ? JPV + zj : (zt == 5 ? JPR + zj : 0));
+    const int sA = zt == 1 ? 1 : 3;
+    const T mA = (zt == 1 || zt == 4 || zt == 5) ? T(1) : T(0);
+    const int oB = zt == 0 ? JVW + zj : (zt == 1 ? JVT : (zt == 4 ? JVV + zj : (zt == 5 ? JVR + zj : 0)));
+    const int sB = zt == 1 ? 1 : 3;
+    const T mB = (zt == 0 || zt == 1 || zt == 4 || zt == 5) ? T(1) : T(0);
+    const T c1 = zt == 0 ? C::h : ((zt == 3 || zt == 5) ? T(1) : T(0));
+    const int i1 = zt == 0 ? 6 + zj : (zt == 3 ? zj : (zt == 5 ? 6 + zj : 0));
+    const T c2 = (zt == 0 || zt == 1) ? T(1) : T(0);
+    const int i2 = zt == 0 ? 9 + zj : 12;
+    const int xi = lane < NXI ? lane : 0;                 // xi index handled by this lane
+    const int xz = e_col(xi);                             // its z index (shuffle source for q_xi)
+    int qoff[4];                                          // Quu^-1 row `lane & 3`, packed lower
+#pragma unroll
+    for (int c = 0; c < 4; c++) qoff[c] = 143 + pk(lane & 3, c);
+    // forward: lane = row of dxi+ (as in the fused solver's rollout)
+    const int rt = lane < 3 ? 0 : (lane < 6 ? 1 : (lane < 9 ? 2 : (lane < 13 ? 3 : 4)));
+    const int rr = lane < 3 ? lane : (lane < 6 ? lane - 3 : 0);
+    const int offT = rt == 0 ? JPT + rr : (rt == 1 ? JVT + rr : 0);
+    const int offV = rt == 0 ? JPV + 3 * rr : (rt == 1 ? JVV + 3 * rr : 0);
+    const int offR = rt == 0 ? JPR + 3 * rr : (rt == 1 ? JVR + 3 * rr : 0);
+    const int offW = rt == 1 ? JVW + 3 * rr : 0;
+    const T mMain = rt <= 1 ? T(1) : T(0), mW = rt == 1 ? T(1) : T(0);
+    const T mSelf = (rt == 0 || rt == 2) ? T(1) : T(0);
+    const T cDu = rt == 2 ? C::h : (rt == 3 ? T(1) : T(0));
+    const int duSrc = 8 * ((rt == 2 ? lane - 6 : lane - 9) & 3);
+    const int r4 = lane >> 3, part = lane & 7;
     __syncwarp();
     mbar_wait(bar, 0);
 
-    // hoisted, stage-parallel: w_k = P_{k+1} d_k   (k = 0..N-2)
+    // ---- hoisted, stage-parallel: w_k = P_{k+1} d_k   (k = 0..N-2) -----------------------------------
     for (int e = lane; e < (N - 1) * NXI; e += 32) {
         const int k = e / NXI, i = e - k * NXI;
-        const T* Pn = FAC + (k + 1) * FAC_WORDS;
-        T acc = T(0);
-#pragma unroll
-        for (int j = 0; j < NXI; j++) acc += Pn[pk(i, j)] * DD[k * NXI + j];
-        WY[k * NXI + i] = acc;
+        WY[e] = sym13_row_dot<T>(FAC + (k + 1) * FAC_WORDS, i, DD + k * NXI, T(0));
     }
     __syncwarp();
 
-    // backward sweep: lane i (< 13) carries p_{k+1}[i] in a register
+    // ---- backward sweep: lane i (< 13) carries p_{k+1}[i] in a register; p_k overwrites w_k -------------
     T pnext = T(0);
     for (int k = N - 1; k >= 0; k--) {
         const T* fk = FAC + k * FAC_WORDS;
         const T* jc = fk + 153;
-        if (lane < NXI) TV[lane] = (k < N - 1) ? pnext + WY[k * NXI + lane] : T(0);
-        __syncwarp();
-        T qz = T(0);   // q~ in z-ordering: g + J' tv
-        if (lane < NZ) qz = GZ[k * NZ + lane] + ((k < N - 1) ? jt_y<T>(jc, TV, lane) : T(0));
-        T qu[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) qu[r] = __shfl_sync(0xffffffffu, qz, r);
-        if (lane < 4) {   // kff = -Quu^-1 q_u
-            T acc = T(0);
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc += fk[143 + pk(lane, c)] * qu[c];
-            KF[k * 4 + lane] = -acc;
+        T qz = GZ[k * NZ + zi];
+        if (k < N - 1) {
+            if (lane < NXI) TV[lane] = pnext + WY[k * NXI + lane];
+            __syncwarp();
+            const T s0 = mA * jc[oA] * TV[0] + mB * jc[oB] * TV[3];
+            const T s1 = mA * jc[oA + sA] * TV[1] + mB * jc[oB + sB] * TV[4];
+            const T s2 = mA * jc[oA + 2 * sA] * TV[2] + mB * jc[oB + 2 * sB] * TV[5];
+            qz += ((s0 + s1) + s2) + (c1 * TV[i1] + c2 * TV[i2]);
         }
-        const T qxi = __shfl_sync(0xffffffffu, qz, e_col(lane < NXI ? lane : 0));
-        if (lane < NXI) {   // p_k = q_xi + K' q_u
-            T acc = qxi;
-#pragma unroll
-            for (int r = 0; r < 4; r++) acc += fk[91 + r * 13 + lane] * qu[r];
-            pnext = acc;
-            PV[k * NXI + lane] = acc;
-        }
+        const T qu0 = __shfl_sync(0xffffffffu, qz, 0), qu1 = __shfl_sync(0xffffffffu, qz, 1);
+        const T qu2 = __shfl_sync(0xffffffffu, qz, 2), qu3 = __shfl_sync(0xffffffffu, qz, 3);
+        const T qxi = __shfl_sync(0xffffffffu, qz, xz);
+        if (lane < 4) KF[k * 4 + lane] = -((fk[qoff[0]] * qu0 + fk[qoff[1]] * qu1) + (fk[qoff[2]] * qu2 + fk[qoff[3]] * qu3));
+        pnext = qxi + ((fk[91 + xi] * qu0 + fk[104 + xi] * qu1) + (fk[117 + xi] * qu2 + fk[130 + xi] * qu3));   // p_k = q_xi + K' q_u
+        if (lane < NXI) WY[k * NXI + lane] = pnext;
         __syncwarp();
     }
 
-    // stage 0: x fixed, u_prev free: dq = -Pqq^-1 p_q
+    // ---- stage 0: x fixed, u_prev free: dq = -Pqq^-1 p_q --------------------------------------------------
     {
         T a[16], l[10], li[4], x[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int c = 0; c <= r; c++) a[4 * r + c] = FAC[pk(9 + r, 9 + c)];
-            x[r] = -PV[9 + r];
+            x[r] = -WY[9 + r];
         }
         chol4<T>(a, l, li);
         fsub4<T>(l, li, x);
         bsub4<T>(l, li, x);
-        if (lane < NXI) DXI[lane] = (lane < 9) ? T(0) : x[lane - 9];
+        if (lane < NXI) DXI[lane] = (lane < 9) ? T(0) : (lane == 9 ? x[0] : (lane == 10 ? x[1] : (lane == 11 ? x[2] : x[3])));
     }
     __syncwarp();
 
-    // forward sweep (dz overwrites g)
+    // ---- forward sweep (dz overwrites g) -----------------------------------------------------------------------
     for (int k = 0; k < N; k++) {
         const T* fk = FAC + k * FAC_WORDS;
         const T* jc = fk + 153;
-        const int r = lane >> 3, part = lane & 7;
-        T acc = T(0);
-        for (int i = part; i < 13; i += 8) acc += fk[91 + r * 13 + i] * DXI[i];
+        const T* kg = fk + 91 + r4 * 13;
+        T acc = kg[part] * DXI[part];
+        if (part < 5) acc += kg[part + 8] * DXI[part + 8];
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += KF[k * 4 + r];
-        T v[13];
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = __shfl_sync(0xffffffffu, acc, 8 * q);
-#pragma unroll
-        for (int q = 0; q < 9; q++) v[4 + q] = DXI[q];
+        acc += KF[k * 4 + r4];
+        const T dw0 = __shfl_sync(0xffffffffu, acc, 0), dw1 = __shfl_sync(0xffffffffu, acc, 8);
+        const T dw2 = __shfl_sync(0xffffffffu, acc, 16), dT = __shfl_sync(0xffffffffu, acc, 24);
         const T du_l = __shfl_sync(0xffffffffu, acc, 8 * (lane & 3));
-        const T du_q = __shfl_sync(0xffffffffu, acc, 8 * ((lane - 9) & 3));
+        const T du_s = __shfl_sync(0xffffffffu, acc, duSrc);
+        const T self = DXI[xi];
         if (lane < NZ) GZ[k * NZ + lane] = (lane < 4) ? du_l : (lane < 8 ? DXI[5 + lane] : DXI[lane - 8]);
         T nxt = T(0);
-        if (k < N - 1 && lane < 13) {
-            if (lane < 9) {
-                nxt = DD[k * NXI + lane];
-#pragma unroll
-                for (int c = 0; c < 13; c++) nxt += f_dense<T>(jc, lane, c) * v[c];
-            } else {
-                nxt = du_q + DD[k * NXI + lane];
-            }
+        if (k < N - 1) {
+            const T m0 = jc[offT] * dT + jc[offV] * DXI[3] + jc[offR] * DXI[6];
+            const T m1 = jc[offV + 1] * DXI[4] + jc[offR + 1] * DXI[7];
+            const T m2 = jc[offV + 2] * DXI[5] + jc[offR + 2] * DXI[8];
+            const T mw = jc[offW] * dw0 + jc[offW + 1] * dw1 + jc[offW + 2] * dw2;
+            nxt = DD[k * NXI + xi] + mSelf * self + cDu * du_s + mMain * ((m0 + m1) + m2) + mW * mw;
         }
         __syncwarp();
-        if (k < N - 1 && lane < 13) DXI[lane] = nxt;
+        if (k < N - 1 && lane < NXI) DXI[lane] = nxt;
         __syncwarp();
     }
 
-    // hoisted, stage-parallel: y_k = P_k dxi_k + p_k   (k = 1..N-1),  y_0 = 0
+    // ---- hoisted, stage-parallel: y_k = P_k dxi_k + p_k   (k = 1..N-1),  y_0 = 0 (in place over p_k) ---------
     for (int e = lane; e < N * NXI; e += 32) {
         const int k = e / NXI, i = e - k * NXI;
         T acc = T(0);
         if (k > 0) {
-            const T* Pk = FAC + k * FAC_WORDS;
-            acc = PV[e];
-#pragma unroll
-            for (int j = 0; j < NXI; j++) acc += Pk[pk(i, j)] * GZ[k * NZ + e_col(j)];
+            const T* dz = GZ + k * NZ;
+            const T x[NXI] = {dz[8], dz[9], dz[10], dz[11], dz[12], dz[13], dz[14], dz[15], dz[16], dz[4], dz[5], dz[6], dz[7]};
+            acc = sym13_row_dot<T>(FAC + k * FAC_WORDS, i, x, WY[e]);
         }
         WY[e] = acc;
     }
