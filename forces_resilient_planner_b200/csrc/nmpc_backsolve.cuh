@@ -90,16 +90,14 @@ template <typename T, int N> struct BsLayout {
 
 __device__ __forceinline__ int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-// y_i = sum_j P[i][j] x[j] for a packed-lower symmetric 13x13: unrolled over j with compile-time
-// triangular offsets, one compare/select per term, three independent chains.
-template <typename T> __device__ __forceinline__ T sym13_row_dot(const T* Pk, int i, const T* x, T init)
+// y_i = sum_j P[i][j] x[j] for a packed-lower symmetric 13x13 with the 13 packed offsets of row i
+// precomputed (poff[j] = pk(i, j)); three independent chains.
+template <typename T> __device__ __forceinline__ T sym13_row_dot(const T* Pk, const int poff[NXI], const T* x, T init)
 {
-    const int rowbase = i * (i + 1) / 2;
     T c0 = init, c1 = T(0), c2 = T(0);
 #pragma unroll
     for (int j = 0; j < NXI; j++) {
-        const int off = (j <= i) ? rowbase + j : j * (j + 1) / 2 + i;
-        const T t = Pk[off] * x[j];
+        const T t = Pk[poff[j]] * x[j];
         if (j % 3 == 0) c0 += t; else if (j % 3 == 1) c1 += t; else c2 += t;
     }
     return (c0 + c1) + c2;
@@ -144,9 +142,6 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
     const int i2 = zt == 0 ? 9 + zj : 12;
     const int xi = lane < NXI ? lane : 0;                 // xi index handled by this lane
     const int xz = e_col(xi);                             // its z index (shuffle source for q_xi)
-    int qoff[4];                                          // Quu^-1 row `lane & 3`, packed lower
-#pragma unroll
-    for (int c = 0; c < 4; c++) qoff[c] = 143 + pk(lane & 3, c);
     // forward: lane = row of dxi+ (as in the fused solver's rollout)
     const int rt = lane < 3 ? 0 : (lane < 6 ? 1 : (lane < 9 ? 2 : (lane < 13 ? 3 : 4)));
     const int rr = lane < 3 ? lane : (lane < 6 ? lane - 3 : 0);
@@ -159,13 +154,23 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
     const T cDu = rt == 2 ? C::h : (rt == 3 ? T(1) : T(0));
     const int duSrc = 8 * ((rt == 2 ? lane - 6 : lane - 9) & 3);
     const int r4 = lane >> 3, part = lane & 7;
+    // hoisted symmetric products: lanes 0..12 -> row `lane` of an even pass stage, lanes 13..25 -> odd
+    const int hrow = lane < 13 ? lane : (lane < 26 ? lane - 13 : 0), hsub = lane < 13 ? 0 : 1;
+    const bool hact = lane < 26;
+    int poff[NXI];
+#pragma unroll
+    for (int j = 0; j < NXI; j++) poff[j] = pk(hrow, j);
+    // uniform 4-term product after the q_u broadcast: lanes 0..12 -> column xi of K (p_k), lanes 16..19 -> row of Quu^-1 (kff)
+    int uoff[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) uoff[c] = (lane >= 16 && lane < 20) ? 143 + pk(lane - 16, c) : 91 + 13 * c + xi;
     __syncwarp();
     mbar_wait(bar, 0);
 
-    // ---- hoisted, stage-parallel: w_k = P_{k+1} d_k   (k = 0..N-2) -----------------------------------
-    for (int e = lane; e < (N - 1) * NXI; e += 32) {
-        const int k = e / NXI, i = e - k * NXI;
-        WY[e] = sym13_row_dot<T>(FAC + (k + 1) * FAC_WORDS, i, DD + k * NXI, T(0));
+    // ---- hoisted, stage-parallel: w_k = P_{k+1} d_k   (k = 0..N-2), two stages per pass --------------
+    for (int k0 = 0; k0 < N - 1; k0 += 2) {
+        const int k = k0 + hsub;
+        if (hact && k < N - 1) WY[k * NXI + hrow] = sym13_row_dot<T>(FAC + (k + 1) * FAC_WORDS, poff, DD + k * NXI, T(0));
     }
     __syncwarp();
 
@@ -186,9 +191,10 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
         const T qu0 = __shfl_sync(0xffffffffu, qz, 0), qu1 = __shfl_sync(0xffffffffu, qz, 1);
         const T qu2 = __shfl_sync(0xffffffffu, qz, 2), qu3 = __shfl_sync(0xffffffffu, qz, 3);
         const T qxi = __shfl_sync(0xffffffffu, qz, xz);
-        if (lane < 4) KF[k * 4 + lane] = -((fk[qoff[0]] * qu0 + fk[qoff[1]] * qu1) + (fk[qoff[2]] * qu2 + fk[qoff[3]] * qu3));
-        pnext = qxi + ((fk[91 + xi] * qu0 + fk[104 + xi] * qu1) + (fk[117 + xi] * qu2 + fk[130 + xi] * qu3));   // p_k = q_xi + K' q_u
+        const T u4 = (fk[uoff[0]] * qu0 + fk[uoff[1]] * qu1) + (fk[uoff[2]] * qu2 + fk[uoff[3]] * qu3);
+        pnext = qxi + u4;                                                // lanes 0..12: p_k = q_xi + K' q_u
         if (lane < NXI) WY[k * NXI + lane] = pnext;
+        else if (lane >= 16 && lane < 20) KF[k * 4 + lane - 16] = -u4;   // lanes 16..19: kff = -Quu^-1 q_u
         __syncwarp();
     }
 
@@ -239,16 +245,15 @@ __global__ void __launch_bounds__(32) kkt_backsolve_kernel(const BacksolveParams
     }
 
     // ---- hoisted, stage-parallel: y_k = P_k dxi_k + p_k   (k = 1..N-1),  y_0 = 0 (in place over p_k) ---------
-    for (int e = lane; e < N * NXI; e += 32) {
-        const int k = e / NXI, i = e - k * NXI;
-        T acc = T(0);
-        if (k > 0) {
+    for (int k0 = 1; k0 < N; k0 += 2) {
+        const int k = k0 + hsub;
+        if (hact && k < N) {
             const T* dz = GZ + k * NZ;
             const T x[NXI] = {dz[8], dz[9], dz[10], dz[11], dz[12], dz[13], dz[14], dz[15], dz[16], dz[4], dz[5], dz[6], dz[7]};
-            acc = sym13_row_dot<T>(FAC + k * FAC_WORDS, i, x, WY[e]);
+            WY[k * NXI + hrow] = sym13_row_dot<T>(FAC + k * FAC_WORDS, poff, x, WY[k * NXI + hrow]);
         }
-        WY[e] = acc;
     }
+    if (lane < NXI) WY[lane] = T(0);
     __syncwarp();
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
