@@ -21,7 +21,7 @@ class NmpcOpts(ctypes.Structure):
 
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
-    "nmpc_default_opts", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
+    "nmpc_default_opts", "nmpc_default_opts_f32", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
     "nmpc_smem_bytes", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
     "nmpc_solve_batch_ex_f64",
     "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_model_eval_host_f64",
@@ -65,9 +65,9 @@ def last_error() -> str:
     return load().nmpc_last_error().decode()
 
 
-def default_opts(**kw) -> NmpcOpts:
+def default_opts(f32: bool = False, **kw) -> NmpcOpts:
     o = NmpcOpts()
-    load().nmpc_default_opts(ctypes.byref(o))
+    (load().nmpc_default_opts_f32 if f32 else load().nmpc_default_opts)(ctypes.byref(o))
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(f"nmpc_opts has no field {k!r}")

@@ -344,6 +344,14 @@ void nmpc_default_opts(nmpc_opts* o)
     o->maxit = 200; o->max_bt = 6;
 }
 
+void nmpc_default_opts_f32(nmpc_opts* o)
+{
+    // what single precision can resolve on this problem (gradients of order 1e2..1e3, slacks that are
+    // differences of O(1) numbers): stationarity 2e-2, complementarity 1e-2 with the barrier held at 1e-3
+    nmpc_default_opts(o);
+    o->tol_stat = 2e-2; o->tol_comp = 1e-2; o->mu_floor = 1e-3;
+}
+
 const char* nmpc_last_error(void) { return g_err; }
 const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a; fused warp-per-problem IPM)"; }
 int nmpc_supported_horizon(int N) { return N == 20 || N == 40; }

@@ -1,0 +1,137 @@
+"""Warm-started receding-horizon stream (BASELINE config 5): B agents replanning in lock-step, the
+whole replan cycle resident on the device.
+
+One replan = the reference's solveNMPC sequence for every agent at once
+(/root/reference/src/resilient_planner/plan_manage/src/nmpc_solver.cpp:346-482):
+
+    shift warm start   x0[i] <- z[i+1], last stage duplicated, xinit <- z[1][8:17]
+                       (forces_normal.cpp:62-97, nmpc_solver.cpp:531-543)   nmpc_shift_warm_start_f64
+    pack parameters    refs, f_ext, yaw refs, tightened corridor rows
+                       (forces_normal.cpp:100-136)                          nmpc_pack_params_f64
+    solve              FORCESNLPsolver_normal_solve for every agent          nmpc_solve_batch_f64
+    failure policy     exit flag != 1 -> that agent cold-starts next cycle   (nmpc_solver.cpp:363-364)
+
+With a perfect-model plant the next initial state is the predicted stage-1 state, exactly what the
+reference feeds back (`xinit = mpc_output[1][8:17]`, not odometry).  The three launches of a replan
+can be captured once into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib, prep, workloads as W
+from .solver import _check
+
+
+class RecedingHorizonStream:
+    def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True):
+        import torch
+        self.torch = torch
+        self.dev = torch.device(device)
+        self.B, self.N, self.mcap = batch.B, batch.N, batch.mcap
+        t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt))).to(self.dev)
+        # static per-agent corridor (one polytope per agent, all stages), raw (untightened) rows
+        A = batch.rows[:, 1, :, 0:3]
+        b_raw = batch.rows[:, 1, :, 3] + np.linalg.norm(A * W.EGO_E, axis=-1)
+        self.poly_A = t(A[:, None]); self.poly_b = t(b_raw[:, None])
+        self.poly_m = t(batch.nrows[:, 1:2], np.int32); self.poly_idx = t(np.zeros((self.B, self.N)), np.int32)
+        self.ellipsoid = t(np.tile(np.diag(W.EGO_E).reshape(1, 1, 9), (self.B, self.N, 1)))
+        self.weights = (7.0, 1.0, 80.0, 12.0, 0.5)
+        # dynamic inputs of a replan (host-generated, uploaded each cycle)
+        self.ref_pos = t(batch.hdr[:, :, 0:3]); self.ref_yaw = t(batch.hdr[:, :, 9]); self.ext_acc = t(batch.hdr[:, 0, 3:6])
+        # solver state on the device
+        self.xinit = t(batch.xinit); self.z0 = t(batch.z0); self.z = torch.empty_like(self.z0)
+        self.hdr = torch.empty((self.B, self.N, 10), dtype=torch.float64, device=self.dev)
+        self.rows = torch.empty((self.B, self.N, self.mcap, 4), dtype=torch.float64, device=self.dev)
+        self.nrows = torch.empty((self.B, self.N), dtype=torch.int32, device=self.dev)
+        self.info_int = torch.zeros((self.B, 4), dtype=torch.int32, device=self.dev)
+        self.info_real = torch.zeros((self.B, 8), dtype=torch.float64, device=self.dev)
+        self.cold_z0 = self.z0.clone(); self.cold_x = self.xinit.clone()
+        self.opts_cold = _lib.default_opts()
+        self.opts_warm = _lib.default_opts(mu0=mu0_warm)
+        self.lib = _lib.load()
+        self.graph = None
+        self.use_graph = use_graph
+        self.cycle = 0
+
+    # -- the three launches of a replan, all on `stream` ---------------------------------------------
+    def _enqueue(self, stream, warm: bool):
+        torch = self.torch
+        if warm:
+            prep.shift_warm_start(self.z, self.xinit, self.z0, wrap_yaw=True, stream=stream)
+        hdr, rows, nrows = self.hdr, self.rows, self.nrows
+        w = (ctypes.c_double * 5)(*self.weights)
+        fn = self.lib.nmpc_pack_params_f64
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p] * 8 + [ctypes.POINTER(ctypes.c_double)] + [ctypes.c_void_p] * 4
+        _check(fn(self.B, self.N, 1, self.mcap, self.mcap, self.ref_pos.data_ptr(), self.ref_yaw.data_ptr(),
+                  self.ext_acc.data_ptr(), self.ellipsoid.data_ptr(), self.poly_A.data_ptr(), self.poly_b.data_ptr(),
+                  self.poly_m.data_ptr(), self.poly_idx.data_ptr(), w, hdr.data_ptr(), rows.data_ptr(),
+                  nrows.data_ptr(), stream.cuda_stream))
+        o = self.opts_warm if warm else self.opts_cold
+        _check(self.lib.nmpc_solve_batch_f64(self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(),
+                                             hdr.data_ptr(), rows.data_ptr(), nrows.data_ptr(), 0, ctypes.byref(o),
+                                             self.z.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr(),
+                                             ctypes.c_void_p(stream.cuda_stream)))
+
+    def replan(self, ref_pos: np.ndarray, ref_yaw: np.ndarray, ext_acc: np.ndarray):
+        """One cycle.  Host arrays in (refs of this cycle), host arrays out (first command, flags).
+
+        Cycle 0 is the cold start; cycle 1 launches the warm sequence directly (which also sets the
+        kernels' function attributes); before cycle 2 the warm sequence is captured into a CUDA graph
+        (capture does not execute) and every later cycle replays it."""
+        torch = self.torch
+        st = torch.cuda.current_stream(self.dev)
+        self.ref_pos.copy_(torch.from_numpy(ref_pos), non_blocking=True)
+        self.ref_yaw.copy_(torch.from_numpy(ref_yaw), non_blocking=True)
+        self.ext_acc.copy_(torch.from_numpy(ext_acc), non_blocking=True)
+        if self.cycle == 0:
+            self._enqueue(st, warm=False)
+        elif self.cycle == 1 or not self.use_graph:
+            self._enqueue(st, warm=True)
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize(self.dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._enqueue(torch.cuda.current_stream(self.dev), warm=True)
+            self.graph.replay()
+        self.cycle += 1
+        cmd = self.z[:, 0, 0:4].cpu().numpy()            # D2H read of the step's result (synchronises)
+        flag = self.info_int[:, 0].cpu().numpy()
+        it = self.info_int[:, 1].cpu().numpy()
+        return cmd, flag, it
+
+    def reset_failed(self, flag: np.ndarray):
+        """Reference failure policy: an agent whose solve failed cold-starts on the next cycle
+        (nmpc_solver.cpp:363-364): its trajectory is replaced by the hover guess at its current state."""
+        bad = np.nonzero(flag != 1)[0]
+        if bad.size:
+            torch = self.torch
+            idx = torch.from_numpy(bad).to(self.dev)
+            x = self.z[idx, 1, 8:17]
+            cold = torch.zeros((bad.size, self.N, 17), dtype=torch.float64, device=self.dev)
+            cold[:, :, 3] = W.HOVER_THRUST_GUESS; cold[:, :, 7] = W.HOVER_THRUST_GUESS
+            cold[:, :, 8:17] = x[:, None, :]
+            self.z[idx] = cold
+        return bad.size
+
+
+def synthetic_refs(batch: W.Batch, step: int, rng: np.random.Generator, ext_acc: np.ndarray, period: int = 20):
+    """References of replan `step` for the config-2 style scenario: the straight-line reference
+    shuttles back and forth along its heading (triangle wave, `period` replans each way) so that a
+    long stream stays inside its corridor; the yaw reference holds its settled value; f_ext
+    random-walks with sigma 0.1 per replan."""
+    hdr = batch.hdr
+    v = (hdr[:, 1, 0:3] - hdr[:, 0, 0:3])                     # reference displacement per stage
+    ph = step % (2 * period)
+    off = ph if ph <= period else 2 * period - ph             # 0..period..0
+    kk = np.arange(batch.N)[None, :, None]
+    # within the horizon the reference keeps moving in the current direction of the shuttle
+    direction = 1.0 if ph < period else -1.0
+    ref = hdr[:, 0:1, 0:3] + (off + direction * kk) * v[:, None, :]
+    yaw = np.repeat(hdr[:, -1:, 9], batch.N, axis=1) if step > 0 else hdr[:, :, 9].copy()
+    ext = np.clip(ext_acc + rng.normal(0.0, 0.1, ext_acc.shape), -2.5, 2.5) if step > 0 else ext_acc
+    return np.ascontiguousarray(ref), np.ascontiguousarray(yaw), np.ascontiguousarray(ext)

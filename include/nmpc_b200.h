@@ -57,6 +57,12 @@ typedef struct nmpc_opts {
 } nmpc_opts;
 
 void nmpc_default_opts(nmpc_opts *o);
+/* options for the *_f32 entry points: the reference tolerances (absolute 1e-4 on gradients of order
+ * 1e2..1e3) are below single-precision resolution; these are the tightest values at which every
+ * BASELINE config-3 problem converges in fp32: tol_stat 2e-2, tol_comp 1e-2, mu_floor 1e-3,
+ * tol_eq / tol_ineq unchanged (1e-4).  Solutions then agree with the fp64 KKT point to ~6e-2
+ * (max) / 3e-3 (median) in z; use the fp64 entry points whenever the reference tolerances matter. */
+void nmpc_default_opts_f32(nmpc_opts *o);
 const char *nmpc_last_error(void);
 const char *nmpc_version(void);
 
