@@ -26,7 +26,8 @@ from .solver import _check
 
 
 class RecedingHorizonStream:
-    def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True):
+    def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True,
+                 wrap_yaw: bool = False):
         import torch
         self.torch = torch
         self.dev = torch.device(device)
@@ -54,13 +55,18 @@ class RecedingHorizonStream:
         self.lib = _lib.load()
         self.graph = None
         self.use_graph = use_graph
+        # The reference wraps each stage's yaw into (-pi, pi] after a solve (nmpc_solver.cpp:531-541) and
+        # recomputes the yaw reference relative to the wrapped value (calculate_yaw, :834-862).  A caller
+        # that keeps its yaw references unwrapped (as synthetic_refs does) must leave the states unwrapped
+        # too, otherwise the warm start asks for a spurious 2*pi rotation.
+        self.wrap_yaw = wrap_yaw
         self.cycle = 0
 
     # -- the three launches of a replan, all on `stream` ---------------------------------------------
     def _enqueue(self, stream, warm: bool):
         torch = self.torch
         if warm:
-            prep.shift_warm_start(self.z, self.xinit, self.z0, wrap_yaw=True, stream=stream)
+            prep.shift_warm_start(self.z, self.xinit, self.z0, wrap_yaw=self.wrap_yaw, stream=stream)
         hdr, rows, nrows = self.hdr, self.rows, self.nrows
         w = (ctypes.c_double * 5)(*self.weights)
         fn = self.lib.nmpc_pack_params_f64
