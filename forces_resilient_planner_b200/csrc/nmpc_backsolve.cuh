@@ -39,14 +39,9 @@ __global__ void __launch_bounds__(32) riccati_factor_kernel(const FactorParams<T
     const int lane = threadIdx.x, b = blockIdx.x;
     if (b >= prm.B) return;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    T* sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
     Solver<T, N> s;
-    s.sm = sm; s.nr = reinterpret_cast<int*>(smem_raw + 16); s.lane = lane; s.mcap = 0; s.RS = 1; s.SS = 1;
+    s.bind(smem_raw, lane, 0);
     s.final_variant = false;
-    s.Z = sm + L::Z; s.DZ = sm + L::DZ; s.ZL = sm + L::ZL; s.ZU = sm + L::ZU; s.G = sm + L::G;
-    s.Y = sm + L::Y; s.P = sm + L::P; s.D = sm + L::D; s.JC = sm + L::JC; s.PHID = sm + L::PHID;
-    s.KG = sm + L::KG; s.KFF = sm + L::KFF; s.HDR = sm + L::HDR;
-    s.ROWS = sm + L::rows_off(); s.S = sm + L::s_off(0); s.LC = sm + L::lc_off(0);
     s.fac_out = prm.fac + (size_t)b * N * FAC_WORDS;
     const uint32_t bytes_phi = N * L::PHI_S * sizeof(T), bytes_jc = N * NJC * sizeof(T);
     if (lane == 0) {

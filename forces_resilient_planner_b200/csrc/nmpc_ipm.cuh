@@ -53,58 +53,81 @@ template <typename T> struct Params {
 };
 
 // ------------------------------------------------------------------ shared-memory layout ---
+// Three groups of arrays (offsets in units of T from the start of the T region):
+//   R  "stage-phase" state: z, z_l, z_u, y, headers, bounds table, corridor slacks/multipliers/rows.
+//      Untouched by the KKT sweeps (Riccati, rollout, costates).
+//   O  sweep-private arrays: Riccati gains K, feed-forward terms and the Riccati scratch.
+//      Dead outside the sweeps.
+//   SH shared by both: dz, gradient, p/y_new, defects, compact Jacobians, Phi diagonals.
+// O is OVERLAID on R: before the sweeps every lane parks its slice of the first NPARK words of R in
+// registers (the sweeps use few registers, the evaluation phases that need many do not run then),
+// and restores it afterwards.  That is 15.6 KB less shared memory per problem (fp64, N = 20) and
+// one more resident warp per SM -- occupancy is what bounds this kernel.
 template <typename T, int N> struct Layout {
     static_assert(N % 4 == 0 && N >= 4 && N <= 64, "horizon must be a multiple of 4 (TMA 16-byte granules)");
     static constexpr int HDR_S = 11;    // padded stage-header stride (bank-conflict free)
     static constexpr int PHI_S = 21;    // 17 diagonal + 3 off-diagonal of the position block + u/u_prev coupling
     static constexpr int NR_BYTES = N * 4;
     static constexpr int HEAD_BYTES = 16 + NR_BYTES;   // mbarrier (8, padded to 16) + nrows
-    // offsets in units of T from the start of the T region
+    // ---- R (fixed part) ----
     static constexpr int Z = 0;
-    static constexpr int DZ = Z + N * NZ;
-    static constexpr int ZL = DZ + N * NZ;
+    static constexpr int ZL = Z + N * NZ;
     static constexpr int ZU = ZL + N * NZ;
-    static constexpr int G = ZU + N * NZ;
-    static constexpr int Y = G + N * NZ;
-    static constexpr int P = Y + N * NXI;
-    static constexpr int D = P + N * NXI;
-    static constexpr int JC = D + N * NXI;
-    static constexpr int PHID = JC + N * NJC;           // last stage's slot unused by the solver
-    static constexpr int KG = PHID + N * PHI_S;
-    static constexpr int KFF = KG + N * 52;
-    static constexpr int HDR = KFF + N * 4;
-    // Riccati / rollout scratch
-    static constexpr int PN = HDR + N * HDR_S;   // 13x13 cost-to-go
+    static constexpr int Y = ZU + N * NXI + N * (NZ - NXI);   // = ZU + N*NZ
+    static constexpr int HDR = Y + N * NXI;
+    static constexpr int BND = HDR + N * HDR_S;               // lb(17) | ub(17)
+    static constexpr int R_FIXED = BND + 2 * NZ;
+    __host__ __device__ static constexpr int row_stride(int mcap) { return 4 * mcap + 1; }
+    __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
+    __host__ __device__ static constexpr int s_off(int) { return R_FIXED; }
+    __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
+    __host__ __device__ static constexpr int rows_off(int mcap) { return R_FIXED + 2 * N * s_stride(mcap); }
+    __host__ __device__ static constexpr int r_end(int mcap) { return rows_off(mcap) + N * row_stride(mcap); }
+    // ---- O (overlay at offset 0): Riccati / rollout scratch first, gains last ----
     static constexpr int FDS = 14;               // row stride of the dense 9x13 dynamics Jacobian wrt (u, x)
+    static constexpr int PN = 0;                 // 13x13 cost-to-go
     static constexpr int FD = PN + 169;
-    static constexpr int PF = FD + 9 * FDS;          // 13x13 = PN(:, x) * FD
+    static constexpr int PF = FD + 9 * FDS;      // 13x13 = PN(:, x) * FD
     static constexpr int GG = PF + 169;          // 13x13 = FD' * PF(x, :)
     static constexpr int TV = GG + 169;          // 13    = p+ + PN d
-    static constexpr int FT = TV + 13;           // 13    = FD' TV(x)
-    static constexpr int QUU = FT + 13;          // 4x4
+    static constexpr int QUU = TV + 13;          // 4x4
     static constexpr int QUR = QUU + 16;         // 4x13  [Q_ux | Q_uq]
     static constexpr int QV = QUR + 52;          // 4
     static constexpr int QXI = QV + 4;           // 13
     static constexpr int YS = QXI + 13;          // 4x13  L^-1 QUR
     static constexpr int Y0 = YS + 52;           // 4     L^-1 QV
     static constexpr int DXI = Y0 + 4;           // 13
-    static constexpr int BND = DXI + 14;         // lb(17) | ub(17)
-    static constexpr int FIXED_END = BND + 2 * NZ;
-    // mcap-dependent tail: ROWS [N][4*mcap+1], S [N][mcap|1], LC [N][mcap|1]
-    __host__ __device__ static constexpr int row_stride(int mcap) { return 4 * mcap + 1; }
-    __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
-    __host__ __device__ static constexpr int rows_off() { return FIXED_END; }
-    __host__ __device__ static constexpr int s_off(int mcap) { return rows_off() + N * row_stride(mcap); }
-    __host__ __device__ static constexpr int lc_off(int mcap) { return s_off(mcap) + N * s_stride(mcap); }
-    __host__ __device__ static constexpr int total_T(int mcap) { return lc_off(mcap) + N * s_stride(mcap); }
+    static constexpr int KFF = DXI + 14;
+    static constexpr int KG = KFF + N * 4;
+    static constexpr int O_END = KG + N * 52;
+    // words parked in registers across the sweeps: at most 64 per lane; if the overlay is larger
+    // (long horizons) the gains are placed in SH instead of being overlaid
+    static constexpr bool KG_OVERLAID = (O_END + 31) / 32 <= 64;
+    static constexpr int O_USED = KG_OVERLAID ? O_END : KG;
+    static constexpr int NPARK_LANE = (O_USED + 31) / 32;
+    static constexpr int NPARK = NPARK_LANE * 32;
+    // ---- SH: starts after max(R, parked overlay), 4-word aligned (16 B for fp32 and fp64 TMA) ----
+    __host__ __device__ static constexpr int sh_off(int mcap)
+    {
+        return ((r_end(mcap) > NPARK ? r_end(mcap) : NPARK) + 3) & ~3;
+    }
+    static constexpr int SH_DZ = 0;
+    static constexpr int SH_G = SH_DZ + N * NZ;
+    static constexpr int SH_P = SH_G + N * NZ;
+    static constexpr int SH_D = SH_P + N * NXI;
+    static constexpr int SH_JC = SH_D + N * NXI;
+    static constexpr int SH_PHID = SH_JC + N * NJC;         // last stage's Jacobian slot unused by the solver
+    static constexpr int SH_KG = SH_PHID + N * PHI_S;       // only when the gains are not overlaid
+    static constexpr int SH_END = SH_KG + (KG_OVERLAID ? 0 : N * 52);
+    __host__ __device__ static constexpr int total_T(int mcap) { return sh_off(mcap) + SH_END; }
     __host__ __device__ static constexpr size_t bytes(int mcap)
     {
         return (size_t)HEAD_BYTES + (size_t)total_T(mcap) * sizeof(T);
     }
-    // TMA staging (stage headers + corridor rows as delivered) aliases DZ.. (dead until init)
-    static constexpr int STG_HDR = DZ;
-    static constexpr int STG_ROWS = DZ + N * 10;
-    __host__ __device__ static constexpr bool staging_fits(int mcap) { return N * 10 + N * mcap * 4 <= PHID - DZ; }
+    // TMA staging (stage headers + corridor rows as delivered) lands at the start of SH (dead until init)
+    static constexpr int STG_HDR = 0;
+    static constexpr int STG_ROWS = N * 10;
+    __host__ __device__ static constexpr bool staging_fits(int mcap) { return N * 10 + N * mcap * 4 <= SH_PHID + N * PHI_S; }
 };
 
 // ------------------------------------------------------------------ small device helpers ---
@@ -234,6 +257,31 @@ template <typename T, int N> struct Solver {
     bool final_variant;
     T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *ROWS, *S, *LC, *BND;
     T* fac_out = nullptr;   // when set, riccati_backward streams the factor (P | K | Quu^-1 | J) to HBM
+
+    __device__ __forceinline__ void bind(unsigned char* smem_raw, int lane_, int mcap_)
+    {
+        sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
+        nr = reinterpret_cast<int*>(smem_raw + 16);
+        lane = lane_; mcap = mcap_;
+        RS = L::row_stride(mcap); SS = L::s_stride(mcap);
+        Z = sm + L::Z; ZL = sm + L::ZL; ZU = sm + L::ZU; Y = sm + L::Y; HDR = sm + L::HDR; BND = sm + L::BND;
+        S = sm + L::s_off(mcap); LC = sm + L::lc_off(mcap); ROWS = sm + L::rows_off(mcap);
+        T* sh = sm + L::sh_off(mcap);
+        DZ = sh + L::SH_DZ; G = sh + L::SH_G; P = sh + L::SH_P; D = sh + L::SH_D; JC = sh + L::SH_JC; PHID = sh + L::SH_PHID;
+        KG = L::KG_OVERLAID ? sm + L::KG : sh + L::SH_KG;
+        KFF = sm + L::KFF;
+    }
+    // registers <-> the slice of R that the sweep-private overlay is about to overwrite
+    __device__ __forceinline__ void park(T (&regs)[L::NPARK_LANE]) const
+    {
+#pragma unroll
+        for (int t = 0; t < L::NPARK_LANE; t++) regs[t] = sm[lane + 32 * t];
+    }
+    __device__ __forceinline__ void unpark(const T (&regs)[L::NPARK_LANE]) const
+    {
+#pragma unroll
+        for (int t = 0; t < L::NPARK_LANE; t++) sm[lane + 32 * t] = regs[t];
+    }
 
     __device__ __forceinline__ int live(int k) const { return k == 0 ? 0 : min(nr[k], mcap); }
 
@@ -759,13 +807,9 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     T* sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
 
     Solver<T, N> s;
-    s.sm = sm; s.nr = nr; s.lane = lane; s.mcap = mcap;
-    s.RS = L::row_stride(mcap); s.SS = L::s_stride(mcap);
+    s.bind(smem_raw, lane, mcap);
     s.final_variant = (prm.variant == 1);
-    s.Z = sm + L::Z; s.DZ = sm + L::DZ; s.ZL = sm + L::ZL; s.ZU = sm + L::ZU; s.G = sm + L::G;
-    s.Y = sm + L::Y; s.P = sm + L::P; s.D = sm + L::D; s.JC = sm + L::JC; s.PHID = sm + L::PHID;
-    s.KG = sm + L::KG; s.KFF = sm + L::KFF; s.HDR = sm + L::HDR; s.BND = sm + L::BND;
-    s.ROWS = sm + L::rows_off(); s.S = sm + L::s_off(mcap); s.LC = sm + L::lc_off(mcap);
+    T* const stg = sm + L::sh_off(mcap);   // TMA staging area = start of SH
     const Opts& o = prm.o;
 
     // ---- stage the problem into shared memory with TMA bulk copies ------------------------
@@ -775,8 +819,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         mbar_init(bar, 1);
         mbar_expect_tx(bar, bytes_z + bytes_h + bytes_r + bytes_n);
         tma_load(s.Z, prm.z0 + (size_t)b * N * NZ, bytes_z, bar);
-        tma_load(sm + L::STG_HDR, prm.hdr + (size_t)b * N * 10, bytes_h, bar);
-        if (bytes_r) tma_load(sm + L::STG_ROWS, prm.rows + (size_t)b * N * mcap * 4, bytes_r, bar);
+        tma_load(stg + L::STG_HDR, prm.hdr + (size_t)b * N * 10, bytes_h, bar);
+        if (bytes_r) tma_load(stg + L::STG_ROWS, prm.rows + (size_t)b * N * mcap * 4, bytes_r, bar);
         tma_load(nr, prm.nrows + (size_t)b * N, bytes_n, bar);
     }
     __syncwarp();
@@ -784,11 +828,11 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     // re-layout headers / rows into bank-conflict-free padded strides
     {
         // headers: N*10 -> N*11 ; the regions do not overlap (HDR lives beyond the staging alias)
-        for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = sm[L::STG_HDR + e];
+        for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = stg[L::STG_HDR + e];
         const int nrw = N * mcap * 4;
         for (int e = lane; e < nrw; e += 32) {
             const int k = e / (mcap * 4), q = e - k * mcap * 4;
-            s.ROWS[k * s.RS + q] = sm[L::STG_ROWS + e];
+            s.ROWS[k * s.RS + q] = stg[L::STG_ROWS + e];
         }
     }
     __syncwarp();
@@ -854,10 +898,19 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         const T mu_t = fmax(sigma * mu, (T)o.mu_floor);
         s.assemble(mu_t);
         __syncwarp();
-        bool ok = s.riccati_backward();
-        ok &= s.rollout();
+        bool ok;
+        {
+            T parked[L::NPARK_LANE];
+            s.park(parked);                 // z, z_l, z_u, y, ... leave shared memory for the sweeps
+            __syncwarp();
+            ok = s.riccati_backward();
+            ok &= s.rollout();
+            s.costates();
+            __syncwarp();
+            s.unpark(parked);
+            __syncwarp();
+        }
         if (!ok) { flag = -5; break; }
-        s.costates();
         const T tau = fmin(fmax(T(0.995), T(1) - mu), T(0.99999));
         T ap, ad;
         s.step_lengths(mu_t, tau, ap, ad);

@@ -146,9 +146,9 @@ def test_edge_cases_rows_and_batch_sizes():
     b0 = W.Batch(b.xinit, b.z0, b.hdr, np.zeros((5, 20, 0, 4)), np.zeros((5, 20), np.int32))   # no corridor at all
     r0 = S.solve_host(b0); c0 = O.solve_batch(b0)
     assert np.all(r0.flag == 1) and np.max(np.abs(r0.z - c0["z"])) < 1e-4
-    # ragged: a different live-row count at every stage, capacity 32 (the ABI maximum is 30 rows)
+    # ragged: a different live-row count at every stage, capacity 30 (the ABI maximum)
     rng = np.random.default_rng(0)
-    b = W.config3(64, mcap=32)
+    b = W.config3(64, mcap=30)
     b.nrows[:] = np.minimum(b.nrows, rng.integers(0, 11, b.nrows.shape)).astype(np.int32)
     _compare(S.solve_host(b), O.solve_batch(b))
     # nrows larger than mcap is clamped, not read out of bounds
@@ -177,7 +177,7 @@ def test_bad_arguments_are_rejected_loudly():
                                        x.ctypes.data, 0, None, x.ctypes.data, x.ctypes.data, x.ctypes.data)
     assert rc == -11 and b"N=21" in lib.nmpc_last_error()
     with pytest.raises(RuntimeError):
-        S.solve_host(W.Batch(b.xinit, b.z0, b.hdr, np.zeros((2, 20, 40, 4)), b.nrows))   # mcap > 32
+        S.solve_host(W.Batch(b.xinit, b.z0, b.hdr, np.zeros((2, 20, 40, 4)), b.nrows))   # mcap > 30
 
 
 def test_warm_start_shift_uses_fewer_iterations():
