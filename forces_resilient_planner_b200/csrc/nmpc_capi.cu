@@ -162,7 +162,8 @@ struct Arena {
 };
 std::mutex g_host_mutex;   // the reference solver is non-reentrant (static workspace); mirror that
 Arena g_arena;
-cudaStream_t g_stream = nullptr;
+constexpr int kHostStreams = 3;
+cudaStream_t g_streams[kHostStreams] = {nullptr, nullptr, nullptr};
 
 inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
@@ -174,7 +175,8 @@ int solve_host(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr
     if (B == 0) return 0;
     if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return fail(NMPC_ERR_ARG, "bad N=%d or mcap=%d", N, mcap);
     std::lock_guard<std::mutex> lock(g_host_mutex);
-    if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostStreams; i++)
+        if (!g_streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
     const size_t n_x = (size_t)B * 9 * sizeof(T), n_z = (size_t)B * N * 17 * sizeof(T);
     const size_t n_h = (size_t)B * N * 10 * sizeof(T), n_r = (size_t)B * N * mcap * 4 * sizeof(T);
     const size_t n_n = (size_t)B * N * sizeof(int), n_ii = (size_t)B * 4 * sizeof(int), n_ir = (size_t)B * 8 * sizeof(T);
@@ -184,19 +186,31 @@ int solve_host(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr
     const size_t o_zo = take(n_z), o_ii = take(n_ii), o_ir = take(n_ir);
     if (int rc = g_arena.reserve(off)) return rc;
     char* base = static_cast<char*>(g_arena.p);
-    CUDA_TRY(cudaMemcpyAsync(base + o_x, xinit, n_x, cudaMemcpyHostToDevice, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(base + o_z, z0, n_z, cudaMemcpyHostToDevice, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(base + o_h, hdr, n_h, cudaMemcpyHostToDevice, g_stream));
-    if (n_r) CUDA_TRY(cudaMemcpyAsync(base + o_r, rows, n_r, cudaMemcpyHostToDevice, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(base + o_n, nrows, n_n, cudaMemcpyHostToDevice, g_stream));
-    int rc = solve_device<T>(B, N, mcap, (const T*)(base + o_x), (const T*)(base + o_z), (const T*)(base + o_h),
-                             (const T*)(base + o_r), (const int*)(base + o_n), variant, opts,
-                             (T*)(base + o_zo), (int*)(base + o_ii), (T*)(base + o_ir), g_stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(z_out, base + o_zo, n_z, cudaMemcpyDeviceToHost, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(info_int, base + o_ii, n_ii, cudaMemcpyDeviceToHost, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(info_real, base + o_ir, n_ir, cudaMemcpyDeviceToHost, g_stream));
-    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    // Large batches are cut into chunks that round-robin over a few streams: the H2D copy of chunk
+    // i+1 and the D2H copy of chunk i-1 overlap the solve of chunk i, and the next chunk's CTAs fill
+    // the tail wave of the previous kernel.  Chunk boundaries are multiples of 2 problems, so every
+    // per-problem block keeps the 16-byte alignment the TMA copies need.
+    const int n_chunks = B >= 2048 ? 4 : 1;
+    const int per = ((B + n_chunks - 1) / n_chunks + 1) & ~1;
+    for (int c = 0, lo = 0; lo < B; c++, lo += per) {
+        const int nb = (B - lo < per) ? B - lo : per;
+        cudaStream_t st = g_streams[c % kHostStreams];
+        const size_t pz = (size_t)N * 17 * sizeof(T), ph = (size_t)N * 10 * sizeof(T), pr = (size_t)N * mcap * 4 * sizeof(T);
+        CUDA_TRY(cudaMemcpyAsync(base + o_x + (size_t)lo * 9 * sizeof(T), xinit + (size_t)lo * 9, (size_t)nb * 9 * sizeof(T), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(base + o_z + lo * pz, z0 + (size_t)lo * N * 17, nb * pz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(base + o_h + lo * ph, hdr + (size_t)lo * N * 10, nb * ph, cudaMemcpyHostToDevice, st));
+        if (pr) CUDA_TRY(cudaMemcpyAsync(base + o_r + lo * pr, rows + (size_t)lo * N * mcap * 4, nb * pr, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(base + o_n + (size_t)lo * N * sizeof(int), nrows + (size_t)lo * N, (size_t)nb * N * sizeof(int), cudaMemcpyHostToDevice, st));
+        int rc = solve_device<T>(nb, N, mcap, (const T*)(base + o_x) + (size_t)lo * 9, (const T*)(base + o_z) + (size_t)lo * N * 17,
+                                 (const T*)(base + o_h) + (size_t)lo * N * 10, (const T*)(base + o_r) + (size_t)lo * N * mcap * 4,
+                                 (const int*)(base + o_n) + (size_t)lo * N, variant, opts, (T*)(base + o_zo) + (size_t)lo * N * 17,
+                                 (int*)(base + o_ii) + (size_t)lo * 4, (T*)(base + o_ir) + (size_t)lo * 8, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(z_out + (size_t)lo * N * 17, base + o_zo + lo * pz, nb * pz, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(info_int + (size_t)lo * 4, base + o_ii + (size_t)lo * 4 * sizeof(int), (size_t)nb * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(info_real + (size_t)lo * 8, base + o_ir + (size_t)lo * 8 * sizeof(T), (size_t)nb * 8 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams; i++) CUDA_TRY(cudaStreamSynchronize(g_streams[i]));
     return 0;
 }
 

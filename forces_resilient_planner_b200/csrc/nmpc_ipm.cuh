@@ -419,17 +419,6 @@ template <typename T, int N> struct Solver {
         }
     }
 
-    // position-block entry of Phi_k in xi-ordering (i, j < 9)
-    __device__ __forceinline__ T phi_xx(const T* phi, int i, int j) const
-    {
-        if (i == j) return phi[8 + i];
-        if (i < 3 && j < 3) {
-            int lo = min(i, j), hi = max(i, j);
-            return phi[17 + lo + hi - 1];   // (0,1)->17, (0,2)->18, (1,2)->19
-        }
-        return T(0);
-    }
-
     // ------------------------------------------------------------- Riccati backward -----
     // Four warp-synchronous phases per stage.  Every lane owns a fixed set of matrix entries
     // (compile-time trip counts, per-lane offsets hoisted out of the stage loop), the dense 9x13

@@ -74,8 +74,6 @@ __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sinco
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
-__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
-__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
 
 // acc = z_B T/m + f_ext - g e3 - kd (v - z_B (z_B.v));  R diag(kd,kd,0) R' = kd (I - z_B z_B')
 // JAC: also Av = da/dv, Ar = da/drpy (row-major 3x3), AT = da/dT.
@@ -249,19 +247,6 @@ template <typename T> __device__ __forceinline__ T jt_y(const T* jc, const T* y,
     int j = i - 14;
     return jc[JPR + j] * y[0] + jc[JPR + 3 + j] * y[1] + jc[JPR + 6 + j] * y[2] + jc[JVR + j] * y[3] +
            jc[JVR + 3 + j] * y[4] + jc[JVR + 6 + j] * y[5] + y[6 + j];
-}
-
-// Dense F = d x+ / d (u(4), x(9)) entry (r in 0..8, c in 0..12) from the compact Jacobian.
-template <typename T> __device__ __forceinline__ T f_dense(const T* jc, int r, int c)
-{
-    using C = Const<T>;
-    const int rb = r / 3, ri = r - 3 * rb;   // row block: 0 pos+, 1 vel+, 2 rpy+
-    if (c < 3) return rb == 1 ? jc[JVW + 3 * ri + c] : (rb == 2 && ri == c ? C::h : T(0));
-    if (c == 3) return rb == 0 ? jc[JPT + ri] : (rb == 1 ? jc[JVT + ri] : T(0));
-    const int cb = (c - 4) / 3, ci = (c - 4) - 3 * cb;   // col block: 0 pos, 1 vel, 2 rpy
-    if (cb == 0) return (rb == 0 && ri == ci) ? T(1) : T(0);
-    if (cb == 1) return rb == 0 ? jc[JPV + 3 * ri + ci] : (rb == 1 ? jc[JVV + 3 * ri + ci] : T(0));
-    return rb == 0 ? jc[JPR + 3 * ri + ci] : (rb == 1 ? jc[JVR + 3 * ri + ci] : (ri == ci ? T(1) : T(0)));
 }
 
 }  // namespace nmpc
