@@ -1,0 +1,14 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck): every kernel once, few problems."""
+import sys
+sys.path.insert(0, ".")
+import numpy as np, torch
+from forces_resilient_planner_b200 import workloads as W, solver as S, kkt, prep
+g = S.solve_host(W.config3(12))
+print("solve", g.flag.tolist(), g.it.tolist())
+g = S.solve_host(W.config4(3, 40))
+print("solve N=40", g.flag.tolist())
+phi, jc, gg, d = kkt.random_kkt_problems(6, 20, seed=1)
+t = lambda a: torch.from_numpy(a).cuda()
+fac, st = kkt.riccati_factor(t(phi), t(jc)); dz, y = kkt.kkt_backsolve(fac, t(gg), t(d))
+torch.cuda.synchronize(); print("kkt", st.tolist(), float(dz.abs().max()))
+z = t(np.random.default_rng(0).normal(size=(5, 20, 17))); x, z0 = prep.shift_warm_start(z); torch.cuda.synchronize(); print("shift ok")

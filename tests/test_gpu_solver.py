@@ -249,3 +249,48 @@ def test_receding_horizon_stream_matches_cpu_closed_loop():
         assert np.max(np.abs(cmd - c["z"][:, 0, 0:4])) < 1e-7, step
         xinit, z0 = W.shift_warm_start(c["z"])
     assert s.graph is not None
+
+
+def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows():
+    """The reference layout allows 30 rows per stage; DecompROS polytopes can also leave zero rows in
+    the middle once tightened rows are dropped upstream.  The shim compacts them; the result must
+    equal the native batched call on the compacted problem."""
+    rng = np.random.default_rng(4)
+    b = W.config3(2, mcap=30)
+    w = forces.FORCESNormal()
+    for i in range(b.B):
+        xinit, x0, allp = W.to_forces_params(b, i)
+        allp = allp.reshape(20, 130).copy()
+        # fill up to 30 rows with far-away (inactive) planes, then blank a few at random positions
+        for k in range(20):
+            m = int(b.nrows[i, k])
+            for j in range(m, 30):
+                a = rng.normal(size=3); a /= np.linalg.norm(a)
+                allp[k, 10 + 3 * j:13 + 3 * j] = a
+                allp[k, 100 + j] = a @ b.xinit[i, 0:3] + 50.0
+            for j in rng.choice(np.arange(m, 30), size=5, replace=False):
+                allp[k, 10 + 3 * j:13 + 3 * j] = 0.0; allp[k, 100 + j] = 0.0
+        w.params_.xinit[:] = xinit.tolist(); w.params_.x0[:] = x0.tolist()
+        w.params_.all_parameters[:] = allp.reshape(-1).tolist()
+        assert w.solve_params() == 1
+        # native twin: compact the same rows
+        rows = np.zeros((1, 20, 30, 4)); nrows = np.zeros((1, 20), np.int32)
+        for k in range(20):
+            live = [j for j in range(30) if np.any(allp[k, 10 + 3 * j:13 + 3 * j] != 0) or allp[k, 100 + j] != 0]
+            nrows[0, k] = len(live)
+            for q, j in enumerate(live):
+                rows[0, k, q, 0:3] = allp[k, 10 + 3 * j:13 + 3 * j]; rows[0, k, q, 3] = allp[k, 100 + j]
+        nb = W.Batch(b.xinit[i:i + 1], b.z0[i:i + 1], b.hdr[i:i + 1], rows, nrows, 0)
+        ref = S.solve_host(nb)
+        assert ref.flag[0] == 1 and np.max(np.abs(w.output_array() - ref.z[0])) < 1e-9
+        # inactive far planes must not move the solution away from the original problem's
+        base = S.solve_host(b.slice(i, i + 1))
+        assert np.max(np.abs(base.z[0] - ref.z[0])) < 1e-4
+
+
+def test_large_batch_chunked_host_path_equals_device_path():
+    """B >= 2048 takes the chunked, multi-stream host path; it must return exactly what one launch returns."""
+    b = W.config2(5000)
+    a, c = S.solve(b), S.solve_host(b)
+    assert np.array_equal(a.z, c.z) and np.array_equal(a.flag, c.flag) and np.array_equal(a.it, c.it)
+    assert np.all(a.flag == 1)
