@@ -256,7 +256,7 @@ template <typename T, int N> struct Solver {
     int lane, mcap, RS, SS;
     bool final_variant;
     T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *ROWS, *S, *LC, *BND;
-    T* fac_out = nullptr;   // when set, riccati_backward streams the factor (P | K | Quu^-1 | J) to HBM
+    T* fac_out = nullptr;   // when set, riccati_backward streams the factor ([P: N x 91][K | Quu^-1 | J: N x 113]) to HBM
 
     __device__ __forceinline__ void bind(unsigned char* smem_raw, int lane_, int mcap_)
     {
@@ -582,12 +582,13 @@ template <typename T, int N> struct Solver {
                 if (has1) FD[fdd1] = jcn[lane + 32];
             }
             __syncwarp();
-            if (fac_out) {   // factor block of stage k: [P_k packed lower 91 | K_k 52 | Quu^-1 packed lower 10 | J_k 51]
-                T* fk = fac_out + (size_t)k * FAC_WORDS;
+            if (fac_out) {   // factor of stage k: P_k (91 words, PSYM layout) -> P region; [K_k 52 | Quu^-1 packed lower 10 | J_k 51] -> KQJ region
+                T* fp = fac_out + (size_t)k * 91;
+                T* fk = fac_out + (size_t)N * 91 + (size_t)k * (FAC_WORDS - 91);
 #pragma unroll
                 for (int t = 0; t < 3; t++)
-                    if (lane + 32 * t < 91) fk[lane + 32 * t] = PN[ti[t] * 13 + tj[t]];
-                for (int e = lane; e < 52; e += 32) fk[91 + e] = KG[k * 52 + e];
+                    if (lane + 32 * t < 91) fp[PSYM[ti[t]][tj[t]]] = PN[ti[t] * 13 + tj[t]];
+                for (int e = lane; e < 52; e += 32) fk[e] = KG[k * 52 + e];
                 if (lane < 4) {   // column `lane` of Quu^-1 via the Cholesky factor
                     T x[4];
 #pragma unroll
@@ -596,9 +597,9 @@ template <typename T, int N> struct Solver {
                     bsub4<T>(l, li, x);
 #pragma unroll
                     for (int r = 0; r < 4; r++)
-                        if (r >= lane) fk[143 + r * (r + 1) / 2 + lane] = x[r];
+                        if (r >= lane) fk[52 + r * (r + 1) / 2 + lane] = x[r];
                 }
-                for (int e = lane; e < NJC; e += 32) fk[153 + e] = nx ? JC[k * NJC + e] : T(0);
+                for (int e = lane; e < NJC; e += 32) fk[62 + e] = nx ? JC[k * NJC + e] : T(0);
             }
         }
         return ok;

@@ -20,6 +20,30 @@ constexpr int NXI = 13;   // equalities per transition, c-ordering [x+(9); u(4)]
 constexpr int NJC = 51;   // compact Jacobian words per stage
 constexpr int FAC_WORDS = 204;   // stored Riccati factor per stage: P 91 | K 52 | Quu^-1 10 | J 51
 
+// packed-lower index of a symmetric matrix
+__host__ __device__ __forceinline__ constexpr int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+// Bank-conflict-free packed layout of the symmetric 13x13 cost-to-go matrices in the stored factor:
+// PSYM[i][j] = PSYM[j][i] = word (0..90) holding P[i][j].  For every column j the 13 words
+// {PSYM[i][j]} are distinct mod 16, so a row-per-lane product y = P x reads 13 different 8-byte banks
+// per step (a proper edge colouring of K13 with loops by the 16 banks; scripts/psym_layout.py).
+// Rows padded to 16 bytes so that a lane fetches its row with one 16-byte load.
+__device__ const unsigned char PSYM[13][16] = {
+    { 5,  3, 15,  2,  6, 17, 25, 23, 40, 48, 74, 68, 75, 0, 0, 0},
+    { 3, 21,  9, 10,  7, 28, 33, 24, 32, 46, 45, 63, 86, 0, 0, 0},
+    {15,  9, 19, 12, 11,  0, 42, 14, 54, 34, 55, 72, 84, 0, 0, 0},
+    { 2, 10, 12, 13,  1, 27, 20, 38, 57, 39, 64, 69, 78, 0, 0, 0},
+    { 6,  7, 11,  1, 26, 37,  8, 44, 30, 73, 47, 61, 82, 0, 0, 0},
+    {17, 28,  0, 27, 37,  4, 22, 58, 18, 29, 89, 67, 87, 0, 0, 0},
+    {25, 33, 42, 20,  8, 22, 16, 31, 60, 53, 59, 66, 83, 0, 0, 0},
+    {23, 24, 14, 38, 44, 58, 31, 41, 36, 35, 50, 81, 77, 0, 0, 0},
+    {40, 32, 54, 57, 30, 18, 60, 36, 49, 43, 51, 71, 79, 0, 0, 0},
+    {48, 46, 34, 39, 73, 29, 53, 35, 43, 52, 65, 76, 88, 0, 0, 0},
+    {74, 45, 55, 64, 47, 89, 59, 50, 51, 65, 56, 70, 85, 0, 0, 0},
+    {68, 63, 72, 69, 61, 67, 66, 81, 71, 76, 70, 62, 90, 0, 0, 0},
+    {75, 86, 84, 78, 82, 87, 83, 77, 79, 88, 85, 90, 80, 0, 0, 0},
+};
+
 // compact Jacobian layout (row-major 3x3 blocks unless noted)
 constexpr int JPV = 0;    // d pos+ / d vel
 constexpr int JPR = 9;    // d pos+ / d rpy
