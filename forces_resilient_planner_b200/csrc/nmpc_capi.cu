@@ -61,7 +61,6 @@ template <typename T, int N>
 int launch(const nmpc::Params<T>& prm, cudaStream_t st)
 {
     using L = nmpc::Layout<T, N>;
-    if (!L::staging_fits(prm.mcap)) return fail(NMPC_ERR_ARG, "mcap=%d too large for the staging area", prm.mcap);
     const size_t smem = L::bytes(prm.mcap);
     static thread_local size_t configured = 0;
     if (smem > configured) {

@@ -54,8 +54,10 @@ template <typename T> struct Params {
 
 // ------------------------------------------------------------------ shared-memory layout ---
 // Three groups of arrays (offsets in units of T from the start of the T region):
-//   R  "stage-phase" state: z, z_l, z_u, y, headers, bounds table, corridor slacks/multipliers/rows.
-//      Untouched by the KKT sweeps (Riccati, rollout, costates).
+//   R  "stage-phase" state: z, z_l, z_u, y, headers, bounds table, corridor slacks/multipliers.
+//      Untouched by the KKT sweeps (Riccati, rollout, costates).  The corridor rows themselves are
+//      read-only and identical in every iteration: they stay in global memory and are read through
+//      L1 (32 bytes per row, one row per lane and step) -- that buys the sixth resident warp per SM.
 //   O  sweep-private arrays: Riccati gains K, feed-forward terms and the Riccati scratch.
 //      Dead outside the sweeps.
 //   SH shared by both: dz, gradient, p/y_new, defects, compact Jacobians, Phi diagonals.
@@ -77,12 +79,10 @@ template <typename T, int N> struct Layout {
     static constexpr int HDR = Y + N * NXI;
     static constexpr int BND = HDR + N * HDR_S;               // lb(17) | ub(17)
     static constexpr int R_FIXED = BND + 2 * NZ;
-    __host__ __device__ static constexpr int row_stride(int mcap) { return 4 * mcap + 1; }
     __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
     __host__ __device__ static constexpr int s_off(int) { return R_FIXED; }
     __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
-    __host__ __device__ static constexpr int rows_off(int mcap) { return R_FIXED + 2 * N * s_stride(mcap); }
-    __host__ __device__ static constexpr int r_end(int mcap) { return rows_off(mcap) + N * row_stride(mcap); }
+    __host__ __device__ static constexpr int r_end(int mcap) { return R_FIXED + 2 * N * s_stride(mcap); }
     // ---- O (overlay at offset 0): Riccati / rollout scratch first, gains last ----
     static constexpr int FDS = 14;               // row stride of the dense 9x13 dynamics Jacobian wrt (u, x)
     static constexpr int PN = 0;                 // 13x13 cost-to-go
@@ -124,10 +124,8 @@ template <typename T, int N> struct Layout {
     {
         return (size_t)HEAD_BYTES + (size_t)total_T(mcap) * sizeof(T);
     }
-    // TMA staging (stage headers + corridor rows as delivered) lands at the start of SH (dead until init)
+    // TMA staging (stage headers as delivered) lands at the start of SH (dead until init)
     static constexpr int STG_HDR = 0;
-    static constexpr int STG_ROWS = N * 10;
-    __host__ __device__ static constexpr bool staging_fits(int mcap) { return N * 10 + N * mcap * 4 <= SH_PHID + N * PHI_S; }
 };
 
 // ------------------------------------------------------------------ small device helpers ---
@@ -253,9 +251,10 @@ template <typename T, int N> struct Solver {
     using C = Const<T>;
     T* sm;        // T region
     int* nr;      // live rows per stage
-    int lane, mcap, RS, SS;
+    int lane, mcap, SS;
+    const T* rows_g;   // this problem's corridor rows in global memory, [N][mcap][4] = (a0 a1 a2 b)
     bool final_variant;
-    T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *ROWS, *S, *LC, *BND;
+    T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *S, *LC, *BND;
     T* fac_out = nullptr;   // when set, riccati_backward streams the factor ([P: N x 91][K | Quu^-1 | J: N x 113]) to HBM
 
     __device__ __forceinline__ void bind(unsigned char* smem_raw, int lane_, int mcap_)
@@ -263,9 +262,9 @@ template <typename T, int N> struct Solver {
         sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
         nr = reinterpret_cast<int*>(smem_raw + 16);
         lane = lane_; mcap = mcap_;
-        RS = L::row_stride(mcap); SS = L::s_stride(mcap);
+        SS = L::s_stride(mcap);
         Z = sm + L::Z; ZL = sm + L::ZL; ZU = sm + L::ZU; Y = sm + L::Y; HDR = sm + L::HDR; BND = sm + L::BND;
-        S = sm + L::s_off(mcap); LC = sm + L::lc_off(mcap); ROWS = sm + L::rows_off(mcap);
+        S = sm + L::s_off(mcap); LC = sm + L::lc_off(mcap);
         T* sh = sm + L::sh_off(mcap);
         DZ = sh + L::SH_DZ; G = sh + L::SH_G; P = sh + L::SH_P; D = sh + L::SH_D; JC = sh + L::SH_JC; PHID = sh + L::SH_PHID;
         KG = L::KG_OVERLAID ? sm + L::KG : sh + L::SH_KG;
@@ -284,6 +283,18 @@ template <typename T, int N> struct Solver {
     }
 
     __device__ __forceinline__ int live(int k) const { return k == 0 ? 0 : min(nr[k], mcap); }
+    // corridor row j of stage k: (a0, a1, a2, b), read-only path (LDG.128, L1-resident across iterations)
+    __device__ __forceinline__ void load_row(int k, int j, T (&r)[4]) const
+    {
+        const T* p = rows_g + (size_t)(k * mcap + j) * 4;
+        if constexpr (sizeof(T) == 8) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(p)), c = __ldg(reinterpret_cast<const double2*>(p) + 1);
+            r[0] = a.x; r[1] = a.y; r[2] = c.x; r[3] = c.y;
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        }
+    }
 
     // ---------------------------------------------------------------- model evaluation ---
     // At z + a dz ("lanes = stages"): cost, gradient, compact Jacobian, defects, theta and the barrier
@@ -321,7 +332,7 @@ template <typename T, int N> struct Solver {
             }
             const int m = live(k);
             for (int j = 0; j < m; j++) {
-                const T* r = ROWS + k * RS + 4 * j;
+                T r[4]; load_row(k, j, r);
                 T sj = S[k * SS + j];
                 T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T adz = r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10];
@@ -349,7 +360,7 @@ template <typename T, int N> struct Solver {
             const T* jc = JC + k * NJC;
             T al0 = T(0), al1 = T(0), al2 = T(0);
             for (int j = 0; j < m; j++) {
-                const T* r = ROWS + k * RS + 4 * j;
+                T r[4]; load_row(k, j, r);
                 const T sj = S[k * SS + j], lj = LC[k * SS + j];
                 al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
@@ -404,7 +415,7 @@ template <typename T, int N> struct Solver {
             T o01 = T(0), o02 = T(0), o12 = T(0), d0 = T(0), d1 = T(0), d2 = T(0), g0 = T(0), g1 = T(0), g2 = T(0);
             const int m = live(k);
             for (int j = 0; j < m; j++) {
-                const T* r = ROWS + k * RS + 4 * j;
+                T r[4]; load_row(k, j, r);
                 const T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T sg = lj * is, tt = (mu_t + lj * rc) * is;
@@ -728,7 +739,7 @@ template <typename T, int N> struct Solver {
         for (int k = lane; k < N; k += 32) {
             const int m = live(k);
             for (int j = 0; j < m; j++) {
-                const T* r = ROWS + k * RS + 4 * j;
+                T r[4]; load_row(k, j, r);
                 const T sj = S[k * SS + j], lj = LC[k * SS + j];
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
@@ -753,7 +764,7 @@ template <typename T, int N> struct Solver {
         for (int k = lane; k < N; k += 32) {               // corridor rows first: they read the old position
             const int m = live(k);
             for (int j = 0; j < m; j++) {
-                const T* r = ROWS + k * RS + 4 * j;
+                T r[4]; load_row(k, j, r);
                 const T sj = S[k * SS + j], lj = LC[k * SS + j];
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
@@ -803,28 +814,19 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     const Opts& o = prm.o;
 
     // ---- stage the problem into shared memory with TMA bulk copies ------------------------
-    const uint32_t bytes_z = N * NZ * sizeof(T), bytes_h = N * 10 * sizeof(T);
-    const uint32_t bytes_r = (uint32_t)N * mcap * 4 * sizeof(T), bytes_n = N * 4;
+    const uint32_t bytes_z = N * NZ * sizeof(T), bytes_h = N * 10 * sizeof(T), bytes_n = N * 4;
+    s.rows_g = prm.rows + (size_t)b * N * mcap * 4;
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, bytes_z + bytes_h + bytes_r + bytes_n);
+        mbar_expect_tx(bar, bytes_z + bytes_h + bytes_n);
         tma_load(s.Z, prm.z0 + (size_t)b * N * NZ, bytes_z, bar);
         tma_load(stg + L::STG_HDR, prm.hdr + (size_t)b * N * 10, bytes_h, bar);
-        if (bytes_r) tma_load(stg + L::STG_ROWS, prm.rows + (size_t)b * N * mcap * 4, bytes_r, bar);
         tma_load(nr, prm.nrows + (size_t)b * N, bytes_n, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    // re-layout headers / rows into bank-conflict-free padded strides
-    {
-        // headers: N*10 -> N*11 ; the regions do not overlap (HDR lives beyond the staging alias)
-        for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = stg[L::STG_HDR + e];
-        const int nrw = N * mcap * 4;
-        for (int e = lane; e < nrw; e += 32) {
-            const int k = e / (mcap * 4), q = e - k * mcap * 4;
-            s.ROWS[k * s.RS + q] = stg[L::STG_ROWS + e];
-        }
-    }
+    // re-layout the headers into a bank-conflict-free padded stride: N*10 -> N*11 (HDR lives beyond the staging alias)
+    for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = stg[L::STG_HDR + e];
     __syncwarp();
 
     // ---- initial point -------------------------------------------------------------------
@@ -854,7 +856,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         for (int i = 0; i < NXI; i++) s.Y[k * NXI + i] = T(0);
         const int m = s.live(k);
         for (int j = 0; j < m; j++) {
-            const T* r = s.ROWS + k * s.RS + 4 * j;
+            T r[4]; s.load_row(k, j, r);
             T sl = (r[3] + C::hu) - (r[0] * s.Z[k * NZ + 8] + r[1] * s.Z[k * NZ + 9] + r[2] * s.Z[k * NZ + 10]);
             sl = fmax(sl, (T)o.s_floor);
             s.S[k * s.SS + j] = sl;
