@@ -447,6 +447,19 @@ int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double* ref
     return 0;
 }
 
+int nmpc_sample_reference_f64(int B, int N, int P, double Ts, const double* kino_path, const int* kino_size,
+                              const double* t_off, const double* last_yaw, const double* pos1, double* ref_pos,
+                              double* ref_yaw, int* hard_to_follow, void* stream)
+{
+    if (B < 0 || N <= 0 || P <= 0 || !(Ts > 0)) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d P=%d Ts=%g", B, N, P, Ts);
+    if (B == 0) return 0;
+    if (!kino_path || !kino_size || !t_off || !last_yaw || !ref_pos || !ref_yaw) return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::SampleParams q{B, N, P, Ts, kino_path, kino_size, t_off, last_yaw, pos1, ref_pos, ref_yaw, hard_to_follow};
+    nmpc::sample_reference_kernel<<<(B + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int nmpc_shift_warm_start_f64(int B, int N, const double* z_prev, double* xinit, double* z0, int wrap_yaw, void* stream)
 {
     if (B < 0 || N <= 1) return fail(NMPC_ERR_ARG, "bad argument");

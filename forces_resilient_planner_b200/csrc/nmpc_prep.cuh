@@ -12,12 +12,23 @@
 //                            xinit <- previous[1][8:17] (forces_normal.cpp:62-97), yaw wrapped to
 //                            (-pi, pi] as updateFORCESResults does (nmpc_solver.cpp:531-541)
 //
-// Both are pure data movement plus a few flops per row: one thread per (problem, stage), reads
-// and writes coalesced along the stage-major innermost dimension.
+//   sample_reference_kernel  reference point and yaw reference of every stage from the front-end's
+//                            polyline (NMPCSolver::getCurTraj, nmpc_solver.cpp:109-142, and
+//                            calculate_yaw, :834-862): linear interpolation at Ts, look-ahead point
+//                            five samples on, heading with unwrap against the previous value and the
+//                            0.2 / 0.8 low-pass -- a recurrence over the stages, so one thread per
+//                            agent walks its horizon
+//
+// The first two are pure data movement plus a few flops per row: one thread per (problem, stage),
+// reads and writes coalesced along the stage-major innermost dimension.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace nmpc {
+
+// the reference's own constant (nmpc_solver.cpp:3, `constexpr double PI = 3.1415926;`): its yaw wrap and
+// unwrap use this truncated value, so results are only identical to the reference's with it
+constexpr double REF_PI = 3.1415926;
 
 struct PackParams {
     int B, N, P, M, mcap;
@@ -78,7 +89,7 @@ __global__ void shift_warm_start_kernel(int B, int N, const double* z_prev, doub
     const int src = (i + 1 < N) ? i + 1 : N - 1;
     const double* zs = z_prev + ((size_t)b * N + src) * 17;
     double* zd = z0 + (size_t)t * 17;
-    const double pi = 3.14159265358979323846;
+    const double pi = REF_PI;
     for (int j = 0; j < 17; j++) {
         double v = zs[j];
         if (j == 16 && wrap_yaw) v = v < -pi ? v + 2 * pi : (v > pi ? v - 2 * pi : v);
@@ -86,6 +97,61 @@ __global__ void shift_warm_start_kernel(int B, int N, const double* z_prev, doub
     }
     if (i == 0)
         for (int j = 0; j < 9; j++) xinit[(size_t)b * 9 + j] = zd[8 + j];
+}
+
+struct SampleParams {
+    int B, N, P;
+    double Ts;
+    const double* kino_path;   // [B][P][3]  front-end path sampled at Ts (kino_path_, nmpc_solver.cpp:215)
+    const int* kino_size;      // [B]        live points of each path (>= 1)
+    const double* t_off;       // [B]        mpc_start_time_ - kino_start_time_ in seconds (:111)
+    const double* last_yaw;    // [B]        yaw of the previous plan's stage 1 (setFORCESParams, :486)
+    const double* pos1;        // [B][3] or nullptr: position of the previous plan's stage 1 (:136)
+    double* ref_pos;           // [B][N][3]
+    double* ref_yaw;           // [B][N]
+    int* hard_to_follow;       // [B] or nullptr: 1 when stage 0's reference is > 1 m from pos1 (kino_replan_, :136-140)
+};
+
+__global__ void sample_reference_kernel(const SampleParams q)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= q.B) return;
+    const double* path = q.kino_path + (size_t)b * q.P * 3;
+    const int size = q.kino_size[b];
+    const double toff = q.t_off[b];
+    const double pi = REF_PI;
+    double last = q.last_yaw[b];
+    for (int i = 0; i < q.N; i++) {
+        const double index_time = i * q.Ts + toff;
+        const unsigned ki = (unsigned)(int)(index_time / q.Ts);
+        double r[3], f[3];
+        if (ki + 1 < (unsigned)size) {
+            const double w = fmod(index_time, q.Ts) / q.Ts;
+            for (int c = 0; c < 3; c++) r[c] = path[ki * 3 + c] + w * (path[(ki + 1) * 3 + c] - path[ki * 3 + c]);
+        } else {
+            for (int c = 0; c < 3; c++) r[c] = path[(size - 1) * 3 + c];
+        }
+        const unsigned kf = (ki + 5 < (unsigned)size) ? ki + 5 : (unsigned)(size - 1);
+        for (int c = 0; c < 3; c++) f[c] = path[kf * 3 + c];
+        // calculate_yaw
+        const double dx = f[0] - r[0], dy = f[1] - r[1], dz = f[2] - r[2];
+        const double yaw_temp = sqrt(dx * dx + dy * dy + dz * dz) > 0.1 ? atan2(dy, dx) : last;
+        double yaw = yaw_temp;
+        if (fabs(yaw_temp - last) > pi) yaw = yaw_temp > 0 ? yaw_temp - 2 * pi : yaw_temp + 2 * pi;
+        yaw = 0.2 * last + 0.8 * yaw;
+        last = yaw;
+        double* o = q.ref_pos + ((size_t)b * q.N + i) * 3;
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+        q.ref_yaw[(size_t)b * q.N + i] = yaw;
+        if (i == 0 && q.hard_to_follow) {
+            int far = 0;
+            if (q.pos1) {
+                const double ex = r[0] - q.pos1[b * 3], ey = r[1] - q.pos1[b * 3 + 1], ez = r[2] - q.pos1[b * 3 + 2];
+                far = sqrt(ex * ex + ey * ey + ez * ez) > 1.0;
+            }
+            q.hard_to_follow[b] = far;
+        }
+    }
 }
 
 }  // namespace nmpc

@@ -144,3 +144,37 @@ class FORCESFinal(_ForcesWrapper):
 
     def updateFinal(self, mpc_output):
         self._update(mpc_output)
+
+
+class SolveAcceptance:
+    """Exit-code acceptance policy of NMPCSolver::solveNMPC (nmpc_solver.cpp:398-421); twin of
+    host/forces_wrappers.hpp::SolveAcceptance.  `consume(exit_code)` returns update_result."""
+
+    def __init__(self):
+        self.fail_count = 0
+        self.replan_count = 0
+        self.last_exit_code = 1
+        self.kino_replan = False
+
+    def consume(self, exit_code: int) -> bool:
+        update_result = False
+        self.last_exit_code = exit_code
+        if exit_code == 1:
+            self.fail_count = 0
+            self.replan_count = 0
+            update_result = True
+        else:
+            self.fail_count += 1
+            if self.replan_count > 3 and exit_code == 0:
+                self.fail_count = 0
+                self.replan_count = 0
+                update_result = True
+            elif self.fail_count > 2:
+                self.fail_count = 0
+                self.replan_count += 1
+                self.kino_replan = True
+        return update_result
+
+    def next_solve_is_cold(self, initialized_output: bool = True) -> bool:
+        """nmpc_solver.cpp:363-364: `if (!initialized_output_ || exit_code != 1) initMPCOutput();`"""
+        return (not initialized_output) or self.last_exit_code != 1

@@ -152,6 +152,32 @@ public:
     void updateFinal(MPCDeque& mpc_output) { detail::unpack(output_final_, value_final_, mpc_output); }
 };
 
+// Exit-code acceptance policy of NMPCSolver::solveNMPC (plan_manage/src/nmpc_solver.cpp:398-421):
+// only exit code 1 is a success; a maxit exit (0) is tolerated once more than three replans have been
+// forced; the third consecutive failure forces a front-end replan.  The next solve starts from the
+// cold guess whenever the last exit code was not 1 (:363-364).
+struct SolveAcceptance {
+    int fail_count = 0, replan_count = 0, last_exit_code = 1;
+    bool kino_replan = false;
+    bool consume(int exit_code)   // returns update_result: the planner adopts this solve's output
+    {
+        bool update_result = false;
+        last_exit_code = exit_code;
+        if (exit_code == 1) {
+            fail_count = 0; replan_count = 0; update_result = true;
+        } else {
+            fail_count += 1;
+            if (replan_count > 3 && exit_code == 0) {
+                fail_count = 0; replan_count = 0; update_result = true;
+            } else if (fail_count > 2) {
+                fail_count = 0; replan_count += 1; kino_replan = true;
+            }
+        }
+        return update_result;
+    }
+    bool next_solve_is_cold(bool initialized_output) const { return !initialized_output || last_exit_code != 1; }
+};
+
 // Batched counterpart (new: the reference plans for one vehicle): host-pointer solve of B problems.
 class BatchedNMPC {
 public:

@@ -53,24 +53,24 @@ def shift_warm_start(z_prev, xinit=None, z0=None, wrap_yaw=True, stream=None):
     return xinit, z0
 
 
-def pack_params_reference(ref_pos, ref_yaw, ext_acc, ellipsoid, poly_A, poly_b, poly_m, poly_idx, weights5, mcap):
-    """numpy restatement of the same packing loop (host only; the tests' checker for the kernel)."""
-    B, N, _ = ref_pos.shape
-    hdr = np.zeros((B, N, 10))
-    rows = np.zeros((B, N, mcap, 4))
-    nrows = np.zeros((B, N), np.int32)
-    hdr[:, :, 0:3] = ref_pos
-    hdr[:, :, 3:6] = ext_acc[:, None, :]
-    hdr[:, :, 9] = ref_yaw
-    hdr[:, :, 6], hdr[:, :, 7], hdr[:, :, 8] = weights5[0], weights5[1], weights5[2]
-    hdr[:, -1, 6], hdr[:, -1, 7] = weights5[3], weights5[4]
-    for b in range(B):
-        for i in range(N):
-            pi = int(poly_idx[b, i])
-            m = min(int(poly_m[b, pi]), mcap)
-            A = poly_A[b, pi, :m]
-            E = ellipsoid[b, i].reshape(3, 3)
-            rows[b, i, :m, 0:3] = A
-            rows[b, i, :m, 3] = poly_b[b, pi, :m] - np.linalg.norm(A @ E.T, axis=1)
-            nrows[b, i] = m
-    return hdr, rows, nrows
+def sample_reference(kino_path, kino_size, t_off, last_yaw, N, Ts, pos1=None, stream=None):
+    """Batched getCurTraj + calculate_yaw (nmpc_solver.cpp:109-142, 834-862) on the device.
+
+    kino_path [B,P,3], kino_size [B] (int32), t_off [B], last_yaw [B], pos1 [B,3] or None (cuda tensors)
+    -> ref_pos [B,N,3], ref_yaw [B,N], hard_to_follow [B] (int32)."""
+    import torch
+    lib = _lib.load()
+    B, P, _ = kino_path.shape
+    dev = kino_path.device
+    ref_pos = torch.empty((B, N, 3), dtype=torch.float64, device=dev)
+    ref_yaw = torch.empty((B, N), dtype=torch.float64, device=dev)
+    far = torch.zeros((B,), dtype=torch.int32, device=dev)
+    fn = lib.nmpc_sample_reference_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [ctypes.c_void_p] * 9
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _check(fn(B, int(N), P, float(Ts), kino_path.data_ptr(), kino_size.data_ptr(), t_off.data_ptr(),
+                  last_yaw.data_ptr(), pos1.data_ptr() if pos1 is not None else None, ref_pos.data_ptr(),
+                  ref_yaw.data_ptr(), far.data_ptr(), st.cuda_stream))
+    return ref_pos, ref_yaw, far

@@ -134,6 +134,21 @@ int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double *ref
 int nmpc_shift_warm_start_f64(int B, int N, const double *z_prev, double *xinit, double *z0,
                               int wrap_yaw, void *cuda_stream);
 
+/* ---- reference sampling + yaw reference, device-resident ---------------
+ * Batched NMPCSolver::getCurTraj (plan_manage/src/nmpc_solver.cpp:109-142) + calculate_yaw
+ * (:834-862), as called once per stage by setFORCESParams (:484-493):
+ *   kino_path [B][P][3] the front-end polyline sampled at Ts (kino_path_, :215), kino_size [B] its
+ *   live length (>= 1), t_off [B] = mpc_start_time_ - kino_start_time_ in seconds, last_yaw [B] the
+ *   yaw of the previous plan's stage 1 (:486), pos1 [B][3] its position (may be NULL)
+ *   -> ref_pos [B][N][3] (interpolated; clamped to the last point), ref_yaw [B][N] (heading towards
+ *      the point five samples on, unwrapped against the running value, 0.2/0.8 low-pass),
+ *      hard_to_follow [B] (may be NULL): 1 when stage 0's reference is > 1 m from pos1 (:136-140).
+ * All device pointers.                                                                          */
+int nmpc_sample_reference_f64(int B, int N, int P, double Ts, const double *kino_path,
+                              const int *kino_size, const double *t_off, const double *last_yaw,
+                              const double *pos1, double *ref_pos, double *ref_yaw,
+                              int *hard_to_follow, void *cuda_stream);
+
 /* ---- measured CUDA-core FMA peak (TFLOP/s) of the current device, elem_size 8 (fp64) or 4 (fp32):
  * the roofline denominator for the fused solver kernel, which is FMA-issue/latency bound, not
  * HBM bound (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).                       */

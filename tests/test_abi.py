@@ -64,7 +64,7 @@ def test_default_options_match_the_oracle(cuda_lib):
 def test_metadata_calls_work_without_a_gpu(cuda_lib):
     assert cuda_lib.nmpc_supported_horizon(20) == 1 and cuda_lib.nmpc_supported_horizon(40) == 1
     assert cuda_lib.nmpc_supported_horizon(21) == 0
-    assert 40_000 < cuda_lib.nmpc_smem_bytes(20, 8, 8) < 60_000
+    assert 30_000 < cuda_lib.nmpc_smem_bytes(20, 8, 8) < 60_000
     assert cuda_lib.nmpc_backsolve_factor_words() == 204
     assert b"sm_100a" in cuda_lib.nmpc_version()
 

@@ -5,6 +5,7 @@ import pytest
 
 from forces_resilient_planner_b200 import kkt, prep, workloads as W
 from oracle import oracle as O
+from oracle import prep_np as PN
 
 pytestmark = pytest.mark.gpu
 
@@ -98,7 +99,7 @@ def test_pack_params_matches_reference_loop():
     pidx = rng.integers(0, P, (B, N)).astype(np.int32)
     w5 = (7.0, 1.0, 80.0, 12.0, 0.5)
     hdr, rows, nrows = prep.pack_params(_t(ref_pos), _t(ref_yaw), _t(ext), _t(Emat), _t(A), _t(bb), _t(pm), _t(pidx), w5, mcap)
-    h0, r0, n0 = prep.pack_params_reference(ref_pos, ref_yaw, ext, Emat, A, bb, pm, pidx, w5, mcap)
+    h0, r0, n0 = PN.pack_params_reference(ref_pos, ref_yaw, ext, Emat, A, bb, pm, pidx, w5, mcap)
     assert np.array_equal(nrows.cpu().numpy(), n0) and n0.max() == 30
     assert np.array_equal(hdr.cpu().numpy(), h0)
     assert np.max(np.abs(rows.cpu().numpy() - r0)) < 1e-14
@@ -111,7 +112,28 @@ def test_shift_warm_start_matches_reference_shift():
     x_ref, z_ref = W.shift_warm_start(z)
     assert np.array_equal(z0.cpu().numpy(), z_ref) and np.array_equal(xinit.cpu().numpy(), x_ref)
     xinit, z0 = prep.shift_warm_start(_t(z), wrap_yaw=True)
-    zw = z.copy(); yaw = zw[:, :, 16]
-    zw[:, :, 16] = np.where(yaw < -np.pi, yaw + 2 * np.pi, np.where(yaw > np.pi, yaw - 2 * np.pi, yaw))
-    x_ref, z_ref = W.shift_warm_start(zw)
+    x_ref, z_ref = W.shift_warm_start(PN.wrap_yaw(z))          # the reference's wrap, with its own PI = 3.1415926
     assert np.allclose(z0.cpu().numpy(), z_ref, atol=0, rtol=0) and np.array_equal(xinit.cpu().numpy(), x_ref)
+
+
+def test_sample_reference_matches_getCurTraj_and_calculate_yaw():
+    """Rank 3 of SURVEY §8f: reference sampling + yaw reference, against the loop restatement."""
+    import torch
+    rng = np.random.default_rng(5)
+    B, P, N, Ts = 257, 64, 20, 0.05
+    size = rng.integers(1, P + 1, B).astype(np.int32); size[:4] = (1, 2, 6, P)
+    step = rng.normal(scale=0.06, size=(B, P, 3)); step[:, :, 2] *= 0.2
+    step[::7] *= 0.01                                      # nearly stationary paths: the "dir too short" branch
+    path = np.cumsum(step, axis=1) + rng.uniform(-3, 3, (B, 1, 3))
+    path[1::5, :, 0] = -np.abs(path[1::5, :, 0]) - 1.0     # headings near +-pi: the unwrap branch
+    path[1::5, :, 1] = 0.02 * np.sin(np.arange(P))[None, :] * rng.choice([-1, 1], (len(path[1::5]), 1))
+    path[1::5, :, 0] -= 0.1 * np.arange(P)[None, :]
+    t_off = rng.uniform(0, 2.5, B); t_off[:8] = 0.0
+    last = rng.uniform(-3.1, 3.1, B)
+    pos1 = path[np.arange(B), np.minimum((t_off / Ts).astype(int), size - 1)] + rng.normal(scale=0.7, size=(B, 3))
+    rp, ry, far = prep.sample_reference(_t(path), torch.from_numpy(size).cuda(), _t(t_off), _t(last), N, Ts, pos1=_t(pos1))
+    rp0, ry0, far0 = PN.sample_reference(path, size, t_off, last, N, Ts, pos1=pos1)
+    assert np.max(np.abs(rp.cpu().numpy() - rp0)) < 1e-13
+    assert np.max(np.abs(ry.cpu().numpy() - ry0)) < 1e-12
+    assert np.array_equal(far.cpu().numpy(), far0) and 0 < far0.sum() < B
+    assert np.any(np.abs(np.diff(ry0, axis=1)) > 1.0) or np.any(np.abs(ry0) > PN.REF_PI)   # an unwrap happened

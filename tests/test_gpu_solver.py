@@ -10,6 +10,7 @@ import pytest
 import helpers as H
 from forces_resilient_planner_b200 import _lib, forces, solver as S, workloads as W
 from oracle import oracle as O
+from oracle import prep_np as PN
 from oracle import ref_model
 
 pytestmark = pytest.mark.gpu
@@ -241,7 +242,7 @@ def test_receding_horizon_stream_matches_cpu_closed_loop():
         cmd, flag, it = s.replan(ref, yaw, ext_g)
         # CPU twin of the same cycle
         ref_c, yaw_c, ext_c = ST.synthetic_refs(b, step, rng_b, ext_c)
-        hdr, rows, nrows = prep.pack_params_reference(ref_c, yaw_c, ext_c, E, A, braw, pm, pidx, s.weights, b.mcap)
+        hdr, rows, nrows = PN.pack_params_reference(ref_c, yaw_c, ext_c, E, A, braw, pm, pidx, s.weights, b.mcap)
         cb = W.Batch(xinit, z0, hdr, rows, nrows, 0)
         c = O.solve_batch(cb, opts=O.default_opts(mu0=1.0 if step == 0 else 0.1))
         assert np.all(flag == 1) and np.all(c["flag"] == 1), step

@@ -1,0 +1,87 @@
+"""Host-side pieces around the solve: the numpy restatements in oracle/prep_np.py
+against hand-computed known answers, and the exit-code acceptance policy (Python and C++ twins).  CPU only."""
+import math
+import os
+import subprocess
+
+import numpy as np
+
+from forces_resilient_planner_b200 import forces
+from oracle import prep_np as PN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_sampling_on_a_straight_line():
+    # 1 m/s along +x sampled at Ts = 0.05 (kino_path_), plan starts 0.02 s after the path (t_off)
+    Ts, N, P = 0.05, 20, 40
+    path = np.zeros((1, P, 3)); path[0, :, 0] = 0.05 * np.arange(P); path[0, :, 2] = 1.0
+    rp, ry, far = PN.sample_reference(path, np.array([P]), np.array([0.02]), np.array([0.5]), N, Ts,
+                                      pos1=np.array([[0.02, 0.0, 1.0]]))
+    assert np.allclose(rp[0, :, 0], 0.05 * np.arange(N) + 0.02, atol=1e-12) and np.all(rp[0, :, 2] == 1.0)
+    # heading 0 towards the look-ahead point; low-pass from last_yaw = 0.5: yaw_i = 0.5 * 0.2^(i+1)
+    assert np.allclose(ry[0], 0.5 * 0.2 ** (np.arange(N) + 1), atol=1e-15)
+    assert far[0] == 0
+
+
+def test_reference_sampling_clamps_at_the_path_end_and_flags_a_far_start():
+    Ts, N = 0.05, 20
+    path = np.zeros((1, 8, 3)); path[0, :, 1] = 0.1 * np.arange(8)
+    rp, ry, far = PN.sample_reference(path, np.array([6]), np.array([0.0]), np.array([0.0]), N, Ts,
+                                      pos1=np.array([[2.0, 0.0, 0.0]]))
+    assert np.allclose(rp[0, :5, 1], 0.1 * np.arange(5)) and np.all(rp[0, 5:, 1] == 0.5)   # only 6 live points
+    assert far[0] == 1                                                                       # 2 m away at index 0
+    # once the reference sits on the last point the direction is shorter than 0.1: yaw keeps decaying towards itself
+    assert abs(ry[0, -1] - ry[0, -2]) < 1e-12
+
+
+def test_yaw_unwrap_uses_the_reference_constant():
+    # heading -3.1 rad while the running yaw is +3.0: |diff| > PI  ->  yaw_temp + 2 PI, with PI = 3.1415926
+    Ts = 0.05
+    path = np.zeros((1, 12, 3))
+    ang = -3.1
+    path[0, :, 0] = math.cos(ang) * 0.1 * np.arange(12); path[0, :, 1] = math.sin(ang) * 0.1 * np.arange(12)
+    _, ry, _ = PN.sample_reference(path, np.array([12]), np.array([0.0]), np.array([3.0]), 1, Ts)
+    assert abs(ry[0, 0] - (0.2 * 3.0 + 0.8 * (ang + 2 * 3.1415926))) < 1e-12
+    z = np.zeros((1, 2, 17)); z[0, 0, 16] = 3.2; z[0, 1, 16] = -3.3
+    w = PN.wrap_yaw(z)
+    assert w[0, 0, 16] == 3.2 - 2 * 3.1415926 and w[0, 1, 16] == -3.3 + 2 * 3.1415926
+
+
+def _scenario(policy, codes):
+    return [(policy.consume(c), policy.fail_count, policy.replan_count, policy.kino_replan) for c in codes]
+
+
+def test_acceptance_policy_follows_solveNMPC():
+    p = forces.SolveAcceptance()
+    assert p.consume(1) is True and not p.next_solve_is_cold()
+    # three failures in a row force a front-end replan; the output is not adopted
+    out = _scenario(p, [-7, 0, -6])
+    assert [o[0] for o in out] == [False, False, False] and out[-1][1:] == (0, 1, True)
+    assert p.next_solve_is_cold()
+    # a maxit exit is only tolerated after more than three forced replans
+    p = forces.SolveAcceptance(); p.replan_count = 3
+    assert p.consume(0) is False
+    p.replan_count = 4
+    assert p.consume(0) is True and (p.fail_count, p.replan_count) == (0, 0)
+    p.replan_count = 4
+    assert p.consume(-7) is False                     # any other code never is
+    assert forces.SolveAcceptance().next_solve_is_cold(initialized_output=False)
+
+
+def test_cpp_acceptance_policy_is_the_same(tmp_path):
+    codes = [1, 0, -7, -6, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, -100, 0, 2, 1]
+    src = tmp_path / "acc.cpp"
+    src.write_text('#include "forces_wrappers.hpp"\n#include <cstdio>\nint main(){ resilient_planner::SolveAcceptance p; int codes[] = {'
+                   + ",".join(map(str, codes)) + '};\nfor (int c : codes) { bool u = p.consume(c); '
+                   'std::printf("%d %d %d %d %d\\n", (int)u, p.fail_count, p.replan_count, (int)p.kino_replan, (int)p.next_solve_is_cold(true)); }\nreturn 0; }\n')
+    exe = tmp_path / "acc"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "forces_resilient_planner_b200", "host"), str(src), "-o", str(exe)])
+    got = [tuple(map(int, ln.split())) for ln in subprocess.check_output([str(exe)]).decode().splitlines()]
+    p = forces.SolveAcceptance()
+    want = []
+    for c in codes:
+        u = p.consume(c)
+        want.append((int(u), p.fail_count, p.replan_count, int(p.kino_replan), int(p.next_solve_is_cold(True))))
+    assert got == want
