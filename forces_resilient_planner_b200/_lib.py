@@ -19,6 +19,11 @@ class NmpcOpts(ctypes.Structure):
                 ("maxit", ctypes.c_int), ("max_bt", ctypes.c_int)]
 
 
+class EllipsoidConsts(ctypes.Structure):
+    """struct nmpc_ellipsoid_consts (include/nmpc_b200.h)."""
+    _fields_ = [(n, ctypes.c_double) for n in ("mass", "drag", "ego_r", "ego_h", "ext_noise_bound", "epsilon", "Ts")]
+
+
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
     "nmpc_default_opts", "nmpc_default_opts_f32", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
@@ -28,7 +33,8 @@ EXPORTS = [
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",
     "nmpc_backsolve_algorithmic_bytes",
-    "nmpc_pack_params_f64", "nmpc_shift_warm_start_f64", "nmpc_sample_reference_f64", "nmpc_fma_peak_probe",
+    "nmpc_pack_params_f64", "nmpc_shift_warm_start_f64", "nmpc_sample_reference_f64", "nmpc_default_ellipsoid_consts", "nmpc_propagate_ellipsoids_f64",
+    "nmpc_fma_peak_probe",
     "FORCESNLPsolver_normal_solve", "FORCESNLPsolver_final_solve",
 ]
 

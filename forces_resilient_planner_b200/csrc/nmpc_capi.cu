@@ -19,6 +19,7 @@
 #include "../../include/FORCESNLPsolver_normal.h"
 #include "../../include/nmpc_b200.h"
 #include "nmpc_backsolve.cuh"
+#include "nmpc_ellipsoid.cuh"
 #include "nmpc_ipm.cuh"
 #include "nmpc_prep.cuh"
 
@@ -443,6 +444,29 @@ int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double* ref
                        weights5[0], weights5[1], weights5[2], weights5[3], weights5[4], hdr, rows, nrows};
     const int n = B * N;
     nmpc::pack_params_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+void nmpc_default_ellipsoid_consts(nmpc_ellipsoid_consts* c)
+{
+    c->mass = 0.745319; c->drag = 0.33; c->ego_r = 0.27; c->ego_h = 0.0425;   // rotors_sim.launch:53-70
+    c->ext_noise_bound = 0.5; c->epsilon = 0.06; c->Ts = 0.05;                 // nmpc_solver.cpp:80, nmpc_utils.h:188
+}
+
+int nmpc_propagate_ellipsoids_f64(int B, int N, const double* z, const nmpc_ellipsoid_consts* consts, double* ellipsoid,
+                                  void* stream)
+{
+    if (B < 0 || N <= 0) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
+    if (B == 0) return 0;
+    if (!z || !ellipsoid) return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc_ellipsoid_consts c;
+    if (consts) c = *consts; else nmpc_default_ellipsoid_consts(&c);
+    if (!(c.mass > 0) || !(c.Ts > 0) || !(c.ext_noise_bound > 0) || !(c.epsilon > 0))
+        return fail(NMPC_ERR_ARG, "bad ellipsoid constants");
+    nmpc::EllipsoidParams q{B, N, z, ellipsoid, c.mass, c.drag, c.ego_r, c.ego_h, c.ext_noise_bound, c.epsilon, c.Ts};
+    nmpc::ellipsoid_propagate_kernel<<<(B + nmpc::ELL_WARPS - 1) / nmpc::ELL_WARPS, 32 * nmpc::ELL_WARPS, 0,
+                                       reinterpret_cast<cudaStream_t>(stream)>>>(q);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

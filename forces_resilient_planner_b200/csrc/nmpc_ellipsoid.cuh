@@ -1,0 +1,265 @@
+// nmpc_ellipsoid.cuh -- disturbance-ellipsoid propagation along the previous plan (sm_100a).
+//
+// Batched, device-resident form of the ellipsoid part of NMPCSolver::setFORCESParams
+// (/root/reference/src/resilient_planner/plan_manage/src/nmpc_solver.cpp:484-521) with the functions it
+// calls per stage: updateMatrix (:615-699, linearisation A_t, B_t and the closed loop
+// Phi = A_t + B_t K_t), eulerToRot (:552-564), getDistrEllipsoid (:567-611) and the 3x3 matrix square
+// root (:511-512).  Output: the N shape matrices E_i (ellipsoid_matrices_) that solveNormal uses to
+// tighten the corridor rows (forces_normal.cpp:124-125) -- i.e. the `ellipsoid` input of
+// pack_params_kernel, so shift -> propagate -> pack -> solve stays on the device.
+//
+// Not a port.  The reference solves, per stage and disturbance direction i, the Sylvester equation
+//     Phi X + X Phi' = N_i - exp(-Phi t) N_i exp(-Phi' t),   N_i = t w_i^2 d_i d_i'
+// by complex Schur forms (Bartels-Stewart) and takes two Pade matrix exponentials.  Its solution is
+// the finite-horizon Gramian  X = int_0^t exp(-Phi s) N_i exp(-Phi' s) ds,  which for a rank-one N_i is
+//     X = t^2 w_i^2  U H U',   U = [u_0 .. u_K],  u_j = (-Phi t)^j d_i / j!,   H[j][l] = 1 / (j + l + 1)
+// (term-by-term integration of the two exponential series; ||Phi t|| ~ 1, K = 24 terms reach fp64
+// round-off).  That needs only 9x9 matrix-vector and small matrix-matrix products, which one warp
+// per agent does out of shared memory; exp(Phi t) is the same Taylor series.  oracle/ellipsoid_np.py
+// restates the reference literally (Schur/Sylvester, Pade); the two agree to ~1e-14 relative.
+//
+// One deliberate deviation, in both: the reference accumulates `temp += sqrt(X.trace())` into an
+// uninitialised double (:573, :597 -- undefined behaviour); here temp starts at 0.
+//
+// The stages are a recurrence (Q_init and Q2 carry over), so a warp walks its agent's horizon;
+// lanes split the matrix entries.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace nmpc {
+
+struct EllipsoidParams {
+    int B, N;
+    const double* z;        // [B][N][17]  previous plan (mpc_output_): thrust z[3], vel z[11:14], rpy z[14:17]
+    double* ellipsoid;      // [B][N][9]   E_i row-major
+    double mass, drag, ego_r, ego_h, ext_noise_bound, epsilon, Ts;
+};
+
+// feedback gain K_t of the ancillary controller (nmpc_solver.cpp:28-31), row-major 4x9
+__device__ const double ELL_KT[36] = {
+    -2.0, 5.0, 0.0, -1.0, 4.0, 0.0, -8.0, 0.0, 0.0,
+    -5.0, -2.0, 0.0, -4.0, -1.0, 0.0, 0.0, -8.0, 0.0,
+    -2.0, -2.0, 0.0, -1.0, -1.0, 0.0, 0.0, 0.0, -8.0,
+    0.0, 0.0, -8.0, 0.0, 0.0, -6.0, 0.0, 0.0, 0.0};
+
+constexpr int ELL_K = 24;              // series terms
+constexpr int ELL_KP = ELL_K + 1;
+constexpr int ELL_WARPS = 2;           // agents per CTA (17.3 KB of shared memory each)
+
+// symmetric 3x3 -> principal square root, cyclic Jacobi in registers (E = V sqrt(L) V')
+__device__ __forceinline__ void sqrtm3_sym(const double q[9], double e[9])
+{
+    double a[3][3] = {{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, {q[6], q[7], q[8]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 8; sweep++) {
+#pragma unroll
+        for (int pq = 0; pq < 3; pq++) {
+            const int p = pq == 2 ? 1 : 0, r = pq == 0 ? 1 : 2;
+            const double apq = a[p][r];
+            if (fabs(apq) > 1e-300) {
+                const double theta = (a[r][r] - a[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {   // A <- A J
+                    const double akp = a[k][p], akr = a[k][r];
+                    a[k][p] = c * akp - s * akr; a[k][r] = s * akp + c * akr;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {   // A <- J' A
+                    const double apk = a[p][k], ark = a[r][k];
+                    a[p][k] = c * apk - s * ark; a[r][k] = s * apk + c * ark;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const double vkp = v[k][p], vkr = v[k][r];
+                    v[k][p] = c * vkp - s * vkr; v[k][r] = s * vkp + c * vkr;
+                }
+            }
+        }
+    }
+    const double l0 = sqrt(fmax(a[0][0], 0.0)), l1 = sqrt(fmax(a[1][1], 0.0)), l2 = sqrt(fmax(a[2][2], 0.0));
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) e[3 * i + j] = v[i][0] * l0 * v[j][0] + v[i][1] * l1 * v[j][1] + v[i][2] * l2 * v[j][2];
+}
+
+__global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(const EllipsoidParams q)
+{
+    // per warp: A = Phi t | E = exp(A) | two series terms | Q_origin | temp_Q | U (3 x 9 x KP) | G = U H | X (3 x 81)
+    // | reciprocals 1/(k+1) | scalars of the stage
+    constexpr int O_A = 0, O_E = 81, O_T0 = 162, O_T1 = 243, O_QO = 324, O_TQ = 405, O_U = 486, O_G = O_U + 27 * ELL_KP,
+                  O_X = O_G + 27 * ELL_KP, O_INV = O_X + 243, O_SC = O_INV + 2 * ELL_KP, O_END = O_SC + 32;
+    __shared__ double smem[ELL_WARPS][O_END];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * ELL_WARPS + wid;
+    if (b >= q.B) return;
+    double* S = smem[wid];
+    double *A = S + O_A, *E = S + O_E, *QO = S + O_QO, *TQ = S + O_TQ, *U = S + O_U, *G = S + O_G, *X = S + O_X;
+    double *INV = S + O_INV, *SC = S + O_SC;
+    const double t = q.Ts;
+
+    for (int e = lane; e < 2 * ELL_KP; e += 32) INV[e] = 1.0 / (double)(e + 1);
+    for (int e = lane; e < 81; e += 32) QO[e] = (e / 9 == e % 9) ? q.epsilon * q.epsilon : 0.0;   // Q_init = eps^2 I (:487)
+    double q2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    __syncwarp();
+
+    for (int i = 0; i < q.N; i++) {
+        const double* zi = q.z + ((size_t)b * q.N + i) * 17;
+        const double thrust = zi[3], v1 = zi[11], v2 = zi[12], v3 = zi[13], roll = zi[14], pitch = zi[15], yaw = zi[16];
+        double sr, cr, sp, cp, sy, cy;
+        sincos(roll, &sr, &cr); sincos(pitch, &sp, &cp); sincos(yaw, &sy, &cy);
+        // R = Rz Ry Rx (eulerToRot)
+        const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                             sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                             -sp, cp * sr, cp * cr};
+        // ---- E_i = sqrtm(Q), Q = Q1 (+) Q2 (:503-512); every lane redundantly, lane 0 stores ----
+        {
+            const double er = q.ego_r * q.ego_r, eh = q.ego_h * q.ego_h;
+            double q1[9], qq[9], ee[9];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) q1[3 * r + c] = er * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]) + eh * R[3 * r + 2] * R[3 * c + 2];
+            if (i == 0) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) qq[e] = q1[e];
+            } else {
+                const double beta = sqrt((q1[0] + q1[4] + q1[8]) / (q2[0] + q2[4] + q2[8]));
+#pragma unroll
+                for (int e = 0; e < 9; e++) qq[e] = (1.0 + 1.0 / beta) * q1[e] + (1.0 + beta) * q2[e];
+            }
+            sqrtm3_sym(qq, ee);
+            if (lane < 9) q.ellipsoid[((size_t)b * q.N + i) * 9 + lane] = ee[lane];
+        }
+        // ---- updateMatrix: the stage's scalars -> SC: a[3][3] = At(3:6, 6:9), RDR'[3][3] = At(3:6, 3:6), bt[3] = Bt(3:6, 3) ----
+        if (lane == 0) {
+            const double comb0 = thrust * 1.0 / q.mass, drag = q.drag;
+            const double comb5 = cp * sp, comb6 = cp * sr, comb7 = cp * cr, comb8 = sp * cr, comb9 = sp * sr;
+            const double comb1 = cr * sy - comb9 * cy, comb2 = sr * cy - comb8 * sy;
+            const double comb3 = cr * cy + comb9 * sy, comb4 = sr * sy + comb8 * cy;
+            const double cp2 = cp * cp, sp2 = sp * sp, cy2 = cy * cy, sy2 = sy * sy, sr2 = sr * sr;
+            const double t10 = comb6 * comb4 - comb7 * comb1, t11 = comb3 * comb4 + comb1 * comb2, t12 = comb6 * comb2 - comb7 * comb3;
+            const double t20 = cy * (sp2 - cp2 + cp2 * sr2) + comb9 * comb1;
+            const double t21 = 2 * comb5 * cy * sy - comb6 * (cy * comb3 + sy * comb1);
+            const double t22 = sy * (cp2 - sp2 - cp2 * sr2) + comb9 * comb3;
+            const double t30 = 2 * drag * (comb3 * comb1 - cp2 * cy * sy), t31 = drag * (comb6 * comb3 - comb5 * sy);
+            const double t32 = drag * (comb3 * comb3 - comb1 * comb1 - cp2 * cy2 + cp2 * sy2), t33 = drag * (comb6 * comb1 + comb5 * cy);
+            // a[r][c]: r = vel row (3..5), c = roll / pitch / yaw column (6..8)
+            SC[0] = comb0 * comb1 + drag * (v3 * t10 + v2 * t11 - 2 * v1 * comb4 * comb1);
+            SC[3] = -comb0 * comb3 + drag * (v1 * t11 - v3 * t12 - 2 * v2 * comb3 * comb2);
+            SC[6] = -comb0 * comb6 + drag * (v1 * t10 - v2 * t12 + 2 * v3 * comb7 * comb6);
+            SC[1] = comb0 * comb7 * cy + drag * (v3 * t20 - v2 * t21 - v1 * 2 * (comb5 * cy2 + comb6 * comb1 * cy));
+            SC[4] = comb0 * comb7 * sy - drag * (v3 * t22 - v1 * t21 - v2 * 2 * (comb5 * sy2 - comb6 * comb3 * sy));
+            SC[7] = -comb0 * comb8 + drag * (v1 * t20 - v2 * t22 + v3 * 2 * (comb5 - comb5 * sr2));
+            SC[2] = comb0 * comb2 + (v1 * t30 - v3 * t31 - v2 * t32);
+            SC[5] = comb0 * comb4 + (-v1 * t32 - v3 * t33 - v2 * t30);
+            SC[8] = -v2 * t33 - v1 * t31;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) SC[9 + 3 * r + c] = drag * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]);   // R diag(d,d,0) R'
+            SC[18] = comb4 / q.mass; SC[19] = -comb2 / q.mass; SC[20] = comb7 / q.mass;
+        }
+        __syncwarp();
+        // ---- A = Phi t = (At + Bt Kt) t ;  E = I + A ; T0 = A ----
+        for (int e = lane; e < 81; e += 32) {
+            const int r = e / 9, c = e - 9 * r;
+            double v = 0.0;
+            if (r < 3) v = (c == r + 3) ? 1.0 : 0.0;
+            else if (r < 6) v = (c >= 6 ? SC[3 * (r - 3) + c - 6] : (c >= 3 ? SC[9 + 3 * (r - 3) + c - 3] : 0.0)) + SC[18 + r - 3] * ELL_KT[27 + c];
+            else v = ELL_KT[9 * (r - 6) + c];
+            v *= t;
+            A[e] = v; S[O_T0 + e] = v; E[e] = v + (r == c ? 1.0 : 0.0);
+        }
+        // Krylov seeds u_0 = d_i = e_{3+i}: U[d][row][0]
+        if (lane < 27) U[lane * ELL_KP] = ((lane % 9) == 3 + lane / 9) ? 1.0 : 0.0;
+        __syncwarp();
+        // ---- exp(A) by Taylor, and the Krylov vectors u_j = -A u_{j-1} / j (lanes 0..26 = (direction, row)) ----
+        for (int k = 2, cur = O_T0, nxt = O_T1;; k++) {
+            const double ik = INV[k - 1];        // 1/k
+            if (k <= ELL_K) {
+                for (int e = lane; e < 81; e += 32) {
+                    const int r = e / 9, c = e - 9 * r;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 9; m++) acc += S[cur + 9 * r + m] * A[9 * m + c];
+                    acc *= ik;
+                    S[nxt + e] = acc; E[e] += acc;
+                }
+            }
+            {   // u_{k-1} for k-1 = 1..K
+                const int j = k - 1;
+                if (lane < 27) {
+                    const int d = lane / 9, r = lane - 9 * d;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 9; m++) acc += A[9 * r + m] * U[(9 * d + m) * ELL_KP + j - 1];
+                    U[(9 * d + r) * ELL_KP + j] = -acc * INV[j - 1];
+                }
+            }
+            __syncwarp();
+            if (k > ELL_K) break;
+            const int tmp = cur; cur = nxt; nxt = tmp;
+        }
+        // ---- G = U H (27 x KP), X_d = t^2 w^2 G_d U_d' (3 of 9 x 9) ----
+        for (int e = lane; e < 27 * ELL_KP; e += 32) {
+            const int row = e / ELL_KP, l = e - ELL_KP * row;
+            double acc = 0.0;
+#pragma unroll 5
+            for (int j = 0; j < ELL_KP; j++) acc += U[row * ELL_KP + j] * INV[j + l];
+            G[e] = acc;
+        }
+        __syncwarp();
+        const double tw = t * t * q.ext_noise_bound * q.ext_noise_bound;
+        for (int e = lane; e < 243; e += 32) {
+            const int d = e / 81, rc = e - 81 * d, r = rc / 9, c = rc - 9 * r;
+            double acc = 0.0;
+#pragma unroll 5
+            for (int l = 0; l < ELL_KP; l++) acc += G[(9 * d + r) * ELL_KP + l] * U[(9 * d + c) * ELL_KP + l];
+            X[e] = tw * acc;
+        }
+        __syncwarp();
+        // ---- Qd = temp * sum_d X_d / sqrt(tr X_d), Q_update (:595-603) ----
+        double st[3], temp = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double tr = 0.0;
+#pragma unroll
+            for (int m = 0; m < 9; m++) tr += X[81 * d + 10 * m];
+            st[d] = sqrt(tr); temp += st[d];
+        }
+        for (int e = lane; e < 81; e += 32) TQ[e] = temp * (X[e] / st[0] + X[81 + e] / st[1] + X[162 + e] / st[2]);
+        __syncwarp();
+        {
+            double tro = 0.0, trd = 0.0;
+#pragma unroll
+            for (int m = 0; m < 9; m++) { tro += QO[10 * m]; trd += TQ[10 * m]; }
+            const double beta = sqrt(tro / trd);
+            __syncwarp();
+            for (int e = lane; e < 81; e += 32) QO[e] = (1.0 + 1.0 / beta) * QO[e] + (1.0 + beta) * TQ[e];
+        }
+        __syncwarp();
+        // ---- Q2 = (exp(A) Q_update exp(A)')[0:3, 0:3] (:604-610) ----
+        if (lane < 27) {
+            const int r = lane / 9, c = lane - 9 * r;
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < 9; m++) acc += E[9 * r + m] * QO[9 * m + c];
+            SC[lane] = acc;                       // T1 = E[0:3, :] Q_update  (3 x 9)
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < 9; m++) acc += SC[9 * r + m] * E[9 * c + m];
+                q2[3 * r + c] = acc;
+            }
+        __syncwarp();
+    }
+}
+
+}  // namespace nmpc

@@ -74,3 +74,27 @@ def sample_reference(kino_path, kino_size, t_off, last_yaw, N, Ts, pos1=None, st
                   last_yaw.data_ptr(), pos1.data_ptr() if pos1 is not None else None, ref_pos.data_ptr(),
                   ref_yaw.data_ptr(), far.data_ptr(), st.cuda_stream))
     return ref_pos, ref_yaw, far
+
+
+def propagate_ellipsoids(z, consts=None, out=None, stream=None):
+    """Disturbance-ellipsoid propagation along the previous plan (setFORCESParams / updateMatrix /
+    getDistrEllipsoid, nmpc_solver.cpp:484-521, 567-699) on the device: z [B,N,17] (cuda, float64)
+    -> ellipsoid [B,N,9], the E_i that pack_params takes.  `consts`: dict of nmpc_ellipsoid_consts overrides."""
+    import torch
+    lib = _lib.load()
+    B, N, _ = z.shape
+    c = _lib.EllipsoidConsts()
+    lib.nmpc_default_ellipsoid_consts(ctypes.byref(c))
+    for k, v in (consts or {}).items():
+        if not hasattr(c, k):
+            raise AttributeError(f"nmpc_ellipsoid_consts has no field {k!r}")
+        setattr(c, k, float(v))
+    out = torch.empty((B, N, 9), dtype=torch.float64, device=z.device) if out is None else out
+    fn = lib.nmpc_propagate_ellipsoids_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(_lib.EllipsoidConsts), ctypes.c_void_p,
+                   ctypes.c_void_p]
+    st = stream if stream is not None else torch.cuda.current_stream(z.device)
+    with torch.cuda.device(z.device):
+        _check(fn(B, N, z.data_ptr(), ctypes.byref(c), out.data_ptr(), st.cuda_stream))
+    return out

@@ -149,6 +149,21 @@ int nmpc_sample_reference_f64(int B, int N, int P, double Ts, const double *kino
                               const double *pos1, double *ref_pos, double *ref_yaw,
                               int *hard_to_follow, void *cuda_stream);
 
+/* ---- disturbance-ellipsoid propagation, device-resident ----------------
+ * Batched form of the ellipsoid part of NMPCSolver::setFORCESParams (plan_manage/src/nmpc_solver.cpp:
+ * 484-521) with updateMatrix (:615-699), eulerToRot (:552-564), getDistrEllipsoid (:567-611) and the
+ * 3x3 matrix square root (:511-512):
+ *   z [B][N][17] the previous plan (mpc_output_)  ->  ellipsoid [B][N][9], the shape matrices E_i
+ *   (ellipsoid_matrices_, row-major) that nmpc_pack_params_f64 takes.  Device pointers.
+ * consts == NULL selects nmpc_default_ellipsoid_consts (rotors_sim.launch:53-70, nmpc_utils.h:188).
+ * Deviation from the reference: its accumulator `temp` (:573) is uninitialised; here it starts at 0. */
+typedef struct nmpc_ellipsoid_consts {
+    double mass, drag, ego_r, ego_h, ext_noise_bound, epsilon, Ts;
+} nmpc_ellipsoid_consts;
+void nmpc_default_ellipsoid_consts(nmpc_ellipsoid_consts *c);
+int nmpc_propagate_ellipsoids_f64(int B, int N, const double *z, const nmpc_ellipsoid_consts *consts,
+                                  double *ellipsoid, void *cuda_stream);
+
 /* ---- measured CUDA-core FMA peak (TFLOP/s) of the current device, elem_size 8 (fp64) or 4 (fp32):
  * the roofline denominator for the fused solver kernel, which is FMA-issue/latency bound, not
  * HBM bound (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).                       */

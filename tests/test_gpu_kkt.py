@@ -137,3 +137,27 @@ def test_sample_reference_matches_getCurTraj_and_calculate_yaw():
     assert np.max(np.abs(ry.cpu().numpy() - ry0)) < 1e-12
     assert np.array_equal(far.cpu().numpy(), far0) and 0 < far0.sum() < B
     assert np.any(np.abs(np.diff(ry0, axis=1)) > 1.0) or np.any(np.abs(ry0) > PN.REF_PI)   # an unwrap happened
+
+
+def test_ellipsoid_propagation_matches_the_literal_restatement():
+    """Rank 2 of SURVEY §8f: E_i along a plan, series formulation on the device vs the Schur/Sylvester +
+    Pade restatement of setFORCESParams / updateMatrix / getDistrEllipsoid (oracle/ellipsoid_np.py)."""
+    from oracle import ellipsoid_np as EN
+    b = W.config2(48)
+    z = O.solve_batch(b)["z"]                      # realistic plans: tilted attitudes, non-zero velocities
+    rng = np.random.default_rng(2)
+    z[40:] += rng.normal(scale=0.05, size=z[40:].shape)     # and some off-trajectory states
+    E = prep.propagate_ellipsoids(_t(z)).cpu().numpy().reshape(48, 20, 3, 3)
+    E0 = EN.propagate_batch(z)
+    assert np.max(np.abs(E - E0)) < 1e-11 * np.max(np.abs(E0))
+    assert np.allclose(E, np.swapaxes(E, -1, -2), atol=1e-14)               # symmetric square roots
+    assert np.all(np.linalg.eigvalsh(E) > 0)
+    # stage 0 is the ego ellipsoid rotated into the world frame: E_0 E_0 = R diag(r^2, r^2, h^2) R'
+    R = EN.euler_to_rot(z[0, 0, 14:17])
+    assert np.allclose(E[0, 0] @ E[0, 0], R @ np.diag([0.27 ** 2, 0.27 ** 2, 0.0425 ** 2]) @ R.T, atol=1e-14)
+    # other constants, and the result feeds pack_params unchanged
+    c = dict(mass=0.74, ext_noise_bound=0.3, Ts=0.05)
+    E2 = prep.propagate_ellipsoids(_t(z[:5]), consts=c).cpu().numpy().reshape(5, 20, 3, 3)
+    E20 = EN.propagate_batch(z[:5], EN.EllipsoidConsts(mass=0.74, ext_noise_bound=0.3))
+    assert np.max(np.abs(E2 - E20)) < 1e-11 * np.max(np.abs(E20))
+    assert np.all(np.trace(E2, axis1=-2, axis2=-1)[:, 1:] < np.trace(E[:5], axis1=-2, axis2=-1)[:, 1:])   # smaller noise bound

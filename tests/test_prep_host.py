@@ -85,3 +85,27 @@ def test_cpp_acceptance_policy_is_the_same(tmp_path):
         u = p.consume(c)
         want.append((int(u), p.fail_count, p.replan_count, int(p.kino_replan), int(p.next_solve_is_cold(True))))
     assert got == want
+
+
+def test_ellipsoid_restatement_properties():
+    """oracle/ellipsoid_np.py against facts that do not depend on its own code path."""
+    from oracle import ellipsoid_np as EN
+    c = EN.EllipsoidConsts()
+    z = np.zeros((20, 17)); z[:, 3] = c.mass * 9.81; z[:, 16] = 0.3        # hover, yawed
+    E = EN.propagate(z, c)
+    # stage 0: the ego ellipsoid itself (hover: R = Rz, the disc is rotation invariant)
+    assert np.allclose(E[0], np.diag([c.ego_r, c.ego_r, c.ego_h]), atol=1e-15)
+    # the shape matrices grow monotonically along the horizon (disturbance accumulates)
+    tr = np.trace(E, axis1=1, axis2=2)
+    assert np.all(np.diff(tr) > 0)
+    # the Sylvester solution is the finite-horizon Gramian: check one against numerical quadrature
+    Phi, _ = EN.update_matrix(z[0, 14:17], z[0, 11:14], z[0, 3], c)
+    import scipy.linalg as sla
+    t = c.Ts
+    N0 = np.zeros((9, 9)); N0[3, 3] = t * c.ext_noise_bound ** 2
+    X = sla.solve_sylvester(Phi, Phi.T, N0 - sla.expm(-Phi * t) @ N0 @ sla.expm(-Phi.T * t))
+    xs, ws = np.polynomial.legendre.leggauss(12)
+    Xq = sum(w * 0.5 * t * (sla.expm(-Phi * (0.5 * t * (x + 1))) @ N0 @ sla.expm(-Phi.T * (0.5 * t * (x + 1)))) for x, w in zip(xs, ws))
+    assert np.max(np.abs(X - Xq)) < 1e-12 * np.max(np.abs(X))
+    # closed loop used by the reference is stable at hover (otherwise the Sylvester equation could be singular)
+    assert np.max(np.linalg.eigvals(Phi).real) < 0
