@@ -11,12 +11,15 @@
 // Not a port.  The reference solves, per stage and disturbance direction i, the Sylvester equation
 //     Phi X + X Phi' = N_i - exp(-Phi t) N_i exp(-Phi' t),   N_i = t w_i^2 d_i d_i'
 // by complex Schur forms (Bartels-Stewart) and takes two Pade matrix exponentials.  Its solution is
-// the finite-horizon Gramian  X = int_0^t exp(-Phi s) N_i exp(-Phi' s) ds,  which for a rank-one N_i is
-//     X = t^2 w_i^2  U H U',   U = [u_0 .. u_K],  u_j = (-Phi t)^j d_i / j!,   H[j][l] = 1 / (j + l + 1)
-// (term-by-term integration of the two exponential series; ||Phi t|| ~ 1, K = 24 terms reach fp64
-// round-off).  That needs only 9x9 matrix-vector and small matrix-matrix products, which one warp
-// per agent does out of shared memory; exp(Phi t) is the same Taylor series.  oracle/ellipsoid_np.py
-// restates the reference literally (Schur/Sylvester, Pade); the two agree to ~1e-14 relative.
+// the finite-horizon Gramian  X = int_0^t exp(-Phi s) N_i exp(-Phi' s) ds = t w_i^2 int_0^t v(s) v(s)' ds,
+// v(s) = exp(-Phi s) d_i  (N_i has rank one).  Here: Krylov vectors u_j = (-Phi t)^j d_i / j!  (K = 20
+// terms reach fp64 round-off at ||Phi t|| ~ 1.3), v at the 12 Gauss-Legendre nodes of [0, t] as
+// V = U [xi_q^j], and X = t^2 w_i^2 sum_q (omega_q / 2) v_q v_q'  (the rule is exact for the series product
+// up to degree 23; the remainder is below 1e-14).  Only the first three rows of exp(Phi t) are needed
+// (the position block of exp(Phi t) Q exp(Phi t)'): three more row-vector series instead of a matrix
+// exponential.  Everything is 9x9 matrix-vector work plus two small products, which one warp per agent
+// does out of shared memory.  oracle/ellipsoid_np.py restates the reference literally
+// (Schur/Sylvester, Pade); the two agree to ~1e-13 relative.
 //
 // One deliberate deviation, in both: the reference accumulates `temp += sqrt(X.trace())` into an
 // uninitialised double (:573, :597 -- undefined behaviour); here temp starts at 0.
@@ -42,9 +45,21 @@ __device__ const double ELL_KT[36] = {
     -2.0, -2.0, 0.0, -1.0, -1.0, 0.0, 0.0, 0.0, -8.0,
     0.0, 0.0, -8.0, 0.0, 0.0, -6.0, 0.0, 0.0, 0.0};
 
-constexpr int ELL_K = 24;              // series terms
+constexpr int ELL_K = 20;              // series terms: ||Phi t|| ~ 1.3, 1.3^20 / 20! ~ 1e-16
 constexpr int ELL_KP = ELL_K + 1;
-constexpr int ELL_WARPS = 2;           // agents per CTA (17.3 KB of shared memory each)
+constexpr int ELL_Q = 12;              // Gauss-Legendre nodes on [0, t]: exact to degree 23 of the series product
+constexpr int ELL_WARPS = 3;           // agents per CTA (14.1 KB of shared memory each)
+static_assert(ELL_KP % 3 == 0 && ELL_Q % 2 == 0, "unrolled accumulation chains");
+
+// nodes xi_q in (0, 1) and sqrt(weight_q / 2) of the 12-point Gauss-Legendre rule
+__device__ const double ELL_XI[ELL_Q] = {
+    0.0092196828766403782, 0.047941371814762601, 0.11504866290284765, 0.20634102285669126, 0.31608425050090994,
+    0.43738329574426554, 0.5626167042557344, 0.68391574949909006, 0.79365897714330869, 0.88495133709715235,
+    0.95205862818523745, 0.99078031712335957};
+__device__ const double ELL_SW[ELL_Q] = {
+    0.15358277310055221, 0.23123508167589868, 0.28291193730854342, 0.31872200012163088, 0.3416815304771057,
+    0.35294974558242898, 0.35294974558242898, 0.3416815304771057, 0.31872200012163088, 0.28291193730854342,
+    0.23123508167589868, 0.15358277310055221};
 
 // symmetric 3x3 -> principal square root, cyclic Jacobi in registers (E = V sqrt(L) V')
 __device__ __forceinline__ void sqrtm3_sym(const double q[9], double e[9])
@@ -52,7 +67,9 @@ __device__ __forceinline__ void sqrtm3_sym(const double q[9], double e[9])
     double a[3][3] = {{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, {q[6], q[7], q[8]}};
     double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 #pragma unroll 1
-    for (int sweep = 0; sweep < 8; sweep++) {
+    for (int sweep = 0; sweep < 6; sweep++) {
+        // converged (quadratically) once the off-diagonal mass is below round-off of the trace
+        if (fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]) <= 1e-17 * (fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]))) break;
 #pragma unroll
         for (int pq = 0; pq < 3; pq++) {
             const int p = pq == 2 ? 1 : 0, r = pq == 0 ? 1 : 2;
@@ -88,20 +105,25 @@ __device__ __forceinline__ void sqrtm3_sym(const double q[9], double e[9])
 
 __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(const EllipsoidParams q)
 {
-    // per warp: A = Phi t | E = exp(A) | two series terms | Q_origin | temp_Q | U (3 x 9 x KP) | G = U H | X (3 x 81)
-    // | reciprocals 1/(k+1) | scalars of the stage
-    constexpr int O_A = 0, O_E = 81, O_T0 = 162, O_T1 = 243, O_QO = 324, O_TQ = 405, O_U = 486, O_G = O_U + 27 * ELL_KP,
-                  O_X = O_G + 27 * ELL_KP, O_INV = O_X + 243, O_SC = O_INV + 2 * ELL_KP, O_END = O_SC + 32;
+    // per warp: A = Phi t | Q_origin | Qd | U (3 x 9 x KP) | V (3 x 9 x Q) | X (3 x 81) | node powers sqrt(w_q/2) xi_q^j
+    // | first three rows of exp(A) (3 x 9) | row-series terms (2 x 27) | 1/k | scalars of the stage
+    constexpr int O_A = 0, O_QO = 81, O_TQ = 162, O_U = 243, O_V = O_U + 27 * ELL_KP, O_X = O_V + 27 * ELL_Q,
+                  O_PW = O_X + 243, O_ER = O_PW + ELL_KP * ELL_Q, O_Y0 = O_ER + 27, O_Y1 = O_Y0 + 27, O_INV = O_Y1 + 27,
+                  O_SC = O_INV + ELL_KP + 1, O_END = O_SC + 32;
     __shared__ double smem[ELL_WARPS][O_END];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * ELL_WARPS + wid;
     if (b >= q.B) return;
     double* S = smem[wid];
-    double *A = S + O_A, *E = S + O_E, *QO = S + O_QO, *TQ = S + O_TQ, *U = S + O_U, *G = S + O_G, *X = S + O_X;
-    double *INV = S + O_INV, *SC = S + O_SC;
+    double *A = S + O_A, *QO = S + O_QO, *TQ = S + O_TQ, *U = S + O_U, *V = S + O_V, *X = S + O_X, *PW = S + O_PW;
+    double *ER = S + O_ER, *INV = S + O_INV, *SC = S + O_SC;
     const double t = q.Ts;
 
-    for (int e = lane; e < 2 * ELL_KP; e += 32) INV[e] = 1.0 / (double)(e + 1);
+    for (int e = lane; e < ELL_KP; e += 32) INV[e] = 1.0 / (double)(e + 1);
+    for (int e = lane; e < ELL_Q; e += 32) {       // PW[j][q] = sqrt(w_q / 2) xi_q^j
+        double pw = ELL_SW[e];
+        for (int j = 0; j < ELL_KP; j++) { PW[j * ELL_Q + e] = pw; pw *= ELL_XI[e]; }
+    }
     for (int e = lane; e < 81; e += 32) QO[e] = (e / 9 == e % 9) ? q.epsilon * q.epsilon : 0.0;   // Q_init = eps^2 I (:487)
     double q2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     __syncwarp();
@@ -162,62 +184,66 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
             SC[18] = comb4 / q.mass; SC[19] = -comb2 / q.mass; SC[20] = comb7 / q.mass;
         }
         __syncwarp();
-        // ---- A = Phi t = (At + Bt Kt) t ;  E = I + A ; T0 = A ----
+        // ---- A = Phi t = (At + Bt Kt) t ----
         for (int e = lane; e < 81; e += 32) {
             const int r = e / 9, c = e - 9 * r;
             double v = 0.0;
             if (r < 3) v = (c == r + 3) ? 1.0 : 0.0;
             else if (r < 6) v = (c >= 6 ? SC[3 * (r - 3) + c - 6] : (c >= 3 ? SC[9 + 3 * (r - 3) + c - 3] : 0.0)) + SC[18 + r - 3] * ELL_KT[27 + c];
             else v = ELL_KT[9 * (r - 6) + c];
-            v *= t;
-            A[e] = v; S[O_T0 + e] = v; E[e] = v + (r == c ? 1.0 : 0.0);
+            A[e] = v * t;
         }
-        // Krylov seeds u_0 = d_i = e_{3+i}: U[d][row][0]
-        if (lane < 27) U[lane * ELL_KP] = ((lane % 9) == 3 + lane / 9) ? 1.0 : 0.0;
+        // seeds: u_0 = d_i = e_{3+i} (U[d][row][0]); row r of exp(A): y_0 = e_r' (lanes 0..26 = (d or r, column))
+        double erow = 0.0;
+        if (lane < 27) {
+            const int d = lane / 9, r = lane - 9 * d;
+            U[lane * ELL_KP] = (r == 3 + d) ? 1.0 : 0.0;
+            erow = (r == d) ? 1.0 : 0.0;
+            S[O_Y0 + lane] = erow;
+        }
         __syncwarp();
-        // ---- exp(A) by Taylor, and the Krylov vectors u_j = -A u_{j-1} / j (lanes 0..26 = (direction, row)) ----
-        for (int k = 2, cur = O_T0, nxt = O_T1;; k++) {
-            const double ik = INV[k - 1];        // 1/k
-            if (k <= ELL_K) {
-                for (int e = lane; e < 81; e += 32) {
-                    const int r = e / 9, c = e - 9 * r;
-                    double acc = 0.0;
+        // ---- u_j = -A u_{j-1} / j  and  y_j = y_{j-1} A / j  (exp(A)[r, :] = sum_j y_j), j = 1..K ----
+        for (int j = 1, cur = O_Y0, nxt = O_Y1; j <= ELL_K; j++) {
+            if (lane < 27) {
+                const int d = lane / 9, r = lane - 9 * d;
+                double au = 0.0, ya = 0.0;
 #pragma unroll
-                    for (int m = 0; m < 9; m++) acc += S[cur + 9 * r + m] * A[9 * m + c];
-                    acc *= ik;
-                    S[nxt + e] = acc; E[e] += acc;
+                for (int m = 0; m < 9; m++) {
+                    au += A[9 * r + m] * U[(9 * d + m) * ELL_KP + j - 1];
+                    ya += S[cur + 9 * d + m] * A[9 * m + r];
                 }
-            }
-            {   // u_{k-1} for k-1 = 1..K
-                const int j = k - 1;
-                if (lane < 27) {
-                    const int d = lane / 9, r = lane - 9 * d;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int m = 0; m < 9; m++) acc += A[9 * r + m] * U[(9 * d + m) * ELL_KP + j - 1];
-                    U[(9 * d + r) * ELL_KP + j] = -acc * INV[j - 1];
-                }
+                const double ij = INV[j - 1];
+                U[lane * ELL_KP + j] = -au * ij;
+                ya *= ij;
+                S[nxt + lane] = ya; erow += ya;
             }
             __syncwarp();
-            if (k > ELL_K) break;
             const int tmp = cur; cur = nxt; nxt = tmp;
         }
-        // ---- G = U H (27 x KP), X_d = t^2 w^2 G_d U_d' (3 of 9 x 9) ----
-        for (int e = lane; e < 27 * ELL_KP; e += 32) {
-            const int row = e / ELL_KP, l = e - ELL_KP * row;
-            double acc = 0.0;
-#pragma unroll 5
-            for (int j = 0; j < ELL_KP; j++) acc += U[row * ELL_KP + j] * INV[j + l];
-            G[e] = acc;
+        if (lane < 27) ER[lane] = erow;
+        // ---- V = U PW (27 x Q): v(s_q) sqrt(w_q / 2);  X_d = t^2 w^2 V_d V_d' ----
+        for (int e = lane; e < 27 * ELL_Q; e += 32) {
+            const int row = e / ELL_Q, qq = e - ELL_Q * row;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < ELL_KP; j += 3) {
+                a0 += U[row * ELL_KP + j] * PW[j * ELL_Q + qq];
+                a1 += U[row * ELL_KP + j + 1] * PW[(j + 1) * ELL_Q + qq];
+                a2 += U[row * ELL_KP + j + 2] * PW[(j + 2) * ELL_Q + qq];
+            }
+            V[e] = (a0 + a1) + a2;
         }
         __syncwarp();
         const double tw = t * t * q.ext_noise_bound * q.ext_noise_bound;
         for (int e = lane; e < 243; e += 32) {
             const int d = e / 81, rc = e - 81 * d, r = rc / 9, c = rc - 9 * r;
-            double acc = 0.0;
-#pragma unroll 5
-            for (int l = 0; l < ELL_KP; l++) acc += G[(9 * d + r) * ELL_KP + l] * U[(9 * d + c) * ELL_KP + l];
-            X[e] = tw * acc;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int l = 0; l < ELL_Q; l += 2) {
+                a0 += V[(9 * d + r) * ELL_Q + l] * V[(9 * d + c) * ELL_Q + l];
+                a1 += V[(9 * d + r) * ELL_Q + l + 1] * V[(9 * d + c) * ELL_Q + l + 1];
+            }
+            X[e] = tw * (a0 + a1);
         }
         __syncwarp();
         // ---- Qd = temp * sum_d X_d / sqrt(tr X_d), Q_update (:595-603) ----
@@ -245,8 +271,8 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
             const int r = lane / 9, c = lane - 9 * r;
             double acc = 0.0;
 #pragma unroll
-            for (int m = 0; m < 9; m++) acc += E[9 * r + m] * QO[9 * m + c];
-            SC[lane] = acc;                       // T1 = E[0:3, :] Q_update  (3 x 9)
+            for (int m = 0; m < 9; m++) acc += ER[9 * r + m] * QO[9 * m + c];
+            SC[lane] = acc;                       // T1 = exp(A)[0:3, :] Q_update  (3 x 9)
         }
         __syncwarp();
 #pragma unroll
@@ -255,7 +281,7 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
             for (int c = 0; c < 3; c++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < 9; m++) acc += SC[9 * r + m] * E[9 * c + m];
+                for (int m = 0; m < 9; m++) acc += SC[9 * r + m] * ER[9 * c + m];
                 q2[3 * r + c] = acc;
             }
         __syncwarp();

@@ -6,6 +6,8 @@ One replan = the reference's solveNMPC sequence for every agent at once
 
     shift warm start   x0[i] <- z[i+1], last stage duplicated, xinit <- z[1][8:17]
                        (forces_normal.cpp:62-97, nmpc_solver.cpp:531-543)   nmpc_shift_warm_start_f64
+    ellipsoids         (optional) E_i propagated along the previous plan
+                       (setFORCESParams, nmpc_solver.cpp:484-521)            nmpc_propagate_ellipsoids_f64
     pack parameters    refs, f_ext, yaw refs, tightened corridor rows
                        (forces_normal.cpp:100-136)                          nmpc_pack_params_f64
     solve              FORCESNLPsolver_normal_solve for every agent          nmpc_solve_batch_f64
@@ -27,7 +29,7 @@ from .solver import _check
 
 class RecedingHorizonStream:
     def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True,
-                 wrap_yaw: bool = False):
+                 wrap_yaw: bool = False, dynamic_ellipsoids: bool = False):
         import torch
         self.torch = torch
         self.dev = torch.device(device)
@@ -60,6 +62,11 @@ class RecedingHorizonStream:
         # that keeps its yaw references unwrapped (as synthetic_refs does) must leave the states unwrapped
         # too, otherwise the warm start asks for a spurious 2*pi rotation.
         self.wrap_yaw = wrap_yaw
+        # True: the corridor is tightened with the disturbance ellipsoids propagated along the previous plan
+        # (setFORCESParams, nmpc_solver.cpp:484-521 -> nmpc_propagate_ellipsoids_f64) instead of the static
+        # ego ellipsoid; the cold start propagates along the cold guess, as the reference does after
+        # initMPCOutput (:363-364).
+        self.dynamic_ellipsoids = dynamic_ellipsoids
         self.cycle = 0
 
     # -- the three launches of a replan, all on `stream` ---------------------------------------------
@@ -67,6 +74,8 @@ class RecedingHorizonStream:
         torch = self.torch
         if warm:
             prep.shift_warm_start(self.z, self.xinit, self.z0, wrap_yaw=self.wrap_yaw, stream=stream)
+        if self.dynamic_ellipsoids:
+            prep.propagate_ellipsoids(self.z if warm else self.z0, out=self.ellipsoid, stream=stream)
         hdr, rows, nrows = self.hdr, self.rows, self.nrows
         w = (ctypes.c_double * 5)(*self.weights)
         fn = self.lib.nmpc_pack_params_f64

@@ -12,3 +12,8 @@ t = lambda a: torch.from_numpy(a).cuda()
 fac, st = kkt.riccati_factor(t(phi), t(jc)); dz, y = kkt.kkt_backsolve(fac, t(gg), t(d))
 torch.cuda.synchronize(); print("kkt", st.tolist(), float(dz.abs().max()))
 z = t(np.random.default_rng(0).normal(size=(5, 20, 17))); x, z0 = prep.shift_warm_start(z); torch.cuda.synchronize(); print("shift ok")
+rng = np.random.default_rng(1)
+path = t(np.cumsum(rng.normal(scale=0.05, size=(7, 30, 3)), axis=1)); size = torch.tensor([1, 2, 6, 30, 30, 12, 29], dtype=torch.int32).cuda()
+rp, ry, far = prep.sample_reference(path, size, t(rng.uniform(0, 1, 7)), t(rng.uniform(-3, 3, 7)), 20, 0.05, pos1=t(rng.normal(size=(7, 3))))
+E = prep.propagate_ellipsoids(t(g.z[:3, :20].astype(np.float64).copy()))
+torch.cuda.synchronize(); print("sample + ellipsoids ok", float(E.abs().max()))

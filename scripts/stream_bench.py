@@ -13,10 +13,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--agents", type=int, default=1024)
 ap.add_argument("--replans", type=int, default=500)
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--ellipsoids", action="store_true", help="propagate the disturbance ellipsoids on the device every replan")
 a = ap.parse_args()
 batch = W.config2(a.agents)
 rng = np.random.Generator(np.random.PCG64(W.SEED + 5))
-s = ST.RecedingHorizonStream(batch, use_graph=not a.no_graph)
+s = ST.RecedingHorizonStream(batch, use_graph=not a.no_graph, dynamic_ellipsoids=a.ellipsoids)
 ext = batch.hdr[:, 0, 3:6].copy()
 lat, its, fails, resets = [], [], 0, 0
 for step in range(a.replans):
@@ -33,4 +34,4 @@ print(json.dumps({"config": f"config5: {a.agents} agents x {a.replans} replans, 
                   "latency_ms_mean": float(lat.mean()), "replans_per_sec_per_agent": 1e3 / float(lat.mean()),
                   "agent_solves_per_sec": a.agents * 1e3 / float(lat.mean()), "mean_iterations_warm": float(np.mean(its[2:])),
                   "mean_iterations_cold": float(its[0]), "failed_solves": fails, "cold_restarts": resets,
-                  "cuda_graph": not a.no_graph}))
+                  "cuda_graph": not a.no_graph, "propagated_ellipsoids": a.ellipsoids}))

@@ -252,6 +252,37 @@ def test_receding_horizon_stream_matches_cpu_closed_loop():
     assert s.graph is not None
 
 
+def test_stream_with_propagated_ellipsoids_matches_cpu_closed_loop():
+    """The same loop with the corridor tightened by the disturbance ellipsoids propagated along the
+    previous plan on the device, against the literal CPU restatement."""
+    from forces_resilient_planner_b200 import stream as ST
+    from oracle import ellipsoid_np as EN
+    b = W.config2(6)
+    rng_a, rng_b = (np.random.Generator(np.random.PCG64(11)) for _ in range(2))
+    s = ST.RecedingHorizonStream(b, use_graph=True, dynamic_ellipsoids=True)
+    ext_g = b.hdr[:, 0, 3:6].copy(); ext_c = ext_g.copy()
+    A = b.rows[:, 1, :, 0:3][:, None]; braw = (b.rows[:, 1, :, 3] + np.linalg.norm(b.rows[:, 1, :, 0:3] * W.EGO_E, axis=-1))[:, None]
+    pm = b.nrows[:, 1:2].astype(np.int32); pidx = np.zeros((b.B, b.N), np.int32)
+    xinit, z0 = b.xinit.copy(), b.z0.copy()
+    prev = z0
+    for step in range(5):
+        ref, yaw, ext_g = ST.synthetic_refs(b, step, rng_a, ext_g)
+        cmd, flag, it = s.replan(ref, yaw, ext_g)
+        ref_c, yaw_c, ext_c = ST.synthetic_refs(b, step, rng_b, ext_c)
+        E = EN.propagate_batch(prev).reshape(b.B, b.N, 9)
+        hdr, rows, nrows = PN.pack_params_reference(ref_c, yaw_c, ext_c, E, A, braw, pm, pidx, s.weights, b.mcap)
+        assert np.max(np.abs(s.rows.cpu().numpy() - rows)) < 1e-10, step
+        c = O.solve_batch(W.Batch(xinit, z0, hdr, rows, nrows, 0), opts=O.default_opts(mu0=1.0 if step == 0 else 0.1))
+        assert np.all(flag == 1) and np.all(c["flag"] == 1), step
+        assert np.array_equal(it, c["it"]), step
+        assert np.max(np.abs(cmd - c["z"][:, 0, 0:4])) < 1e-7, step
+        prev = c["z"]
+        xinit, z0 = W.shift_warm_start(c["z"])
+    # the later stages are tightened more than the static ego ellipsoid would
+    static = b.rows[:, 1:, :6, 3]
+    assert np.all(rows[:, 5:, :6, 3] < static[:, 4:] - 0.05)
+
+
 def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows():
     """The reference layout allows 30 rows per stage; DecompROS polytopes can also leave zero rows in
     the middle once tightened rows are dropped upstream.  The shim compacts them; the result must
