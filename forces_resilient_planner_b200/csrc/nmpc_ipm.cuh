@@ -84,11 +84,9 @@ template <typename T, int N> struct Layout {
     __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
     __host__ __device__ static constexpr int r_end(int mcap) { return R_FIXED + 2 * N * s_stride(mcap); }
     // ---- O (overlay at offset 0): Riccati / rollout scratch first, gains last ----
-    static constexpr int FDS = 14;               // row stride of the dense 9x13 dynamics Jacobian wrt (u, x)
     static constexpr int PN = 0;                 // 13x13 cost-to-go
-    static constexpr int FD = PN + 169;
-    static constexpr int PF = FD + 9 * FDS;      // 13x13 = PN(:, x) * FD
-    static constexpr int GG = PF + 169;          // 13x13 = FD' * PF(x, :)
+    static constexpr int PF = PN + 169;          // 13x13 = PN(:, x) * F    (F = d x+ / d(u, x), 9x13, never formed)
+    static constexpr int GG = PF + 169;          // 13x13 = F' * PF(x, :)
     static constexpr int TV = GG + 169;          // 13    = p+ + PN d
     static constexpr int QUU = TV + 13;          // 4x4
     static constexpr int QUR = QUU + 16;         // 4x13  [Q_ux | Q_uq]
@@ -431,30 +429,40 @@ template <typename T, int N> struct Solver {
     }
 
     // ------------------------------------------------------------- Riccati backward -----
-    // Four warp-synchronous phases per stage.  Every lane owns a fixed set of matrix entries
-    // (compile-time trip counts, per-lane offsets hoisted out of the stage loop), the dense 9x13
-    // Jacobian F is refreshed by a table-driven copy of its 51 variable entries (the 0 / 1 / h
-    // pattern is written once), and all dot products run as three independent FMA chains.
+    // Four warp-synchronous phases per stage:
     //   A: PF = P+(:,x) F,  tv = p+ + P+ d           B: Q blocks (F' PF + coupling), q~ vectors
     //   C: 4x4 Cholesky (rsqrt, no divisions), Y = L^-1 [Q_ux Q_uq | q_u], K = -L^-T Y
-    //   D: P_k = blkdiag(Q_xx, Phi_qq) - Y'Y, p_k = q_xi - Y' y0, F <- stage k-1
-    // Returns false on a non-positive pivot.
-    __device__ __forceinline__ static int fd_slot(int c)
-    {   // compact Jacobian word c -> offset in the dense F (v-ordering columns: w0 w1 w2 T p0..2 v0..2 r0..2)
-        constexpr int S = L::FDS;
-        if (c < JPR) return (c / 3) * S + 7 + c % 3;                    // d pos+/d vel
-        if (c < JPT) return ((c - JPR) / 3) * S + 10 + (c - JPR) % 3;   // d pos+/d rpy
-        if (c < JVV) return (c - JPT) * S + 3;                          // d pos+/d T
-        if (c < JVR) return (3 + (c - JVV) / 3) * S + 7 + (c - JVV) % 3;
-        if (c < JVT) return (3 + (c - JVR) / 3) * S + 10 + (c - JVR) % 3;
-        if (c < JVW) return (3 + c - JVT) * S + 3;
-        return (3 + (c - JVW) / 3) * S + (c - JVW) % 3;                 // d vel+/d rates
+    //   D: P_k = blkdiag(Q_xx, Phi_qq) - Y'Y, p_k = q_xi - Y' y0
+    // F = d x+ / d(u, x) is never formed: its 60 non-zeros are the 51 compact Jacobian words plus the
+    // constants 1 and h, in a fixed pattern
+    //     pos+ = pos + Jpv vel + Jpr rpy + JpT T,   vel+ = Jvv vel + Jvr rpy + JvT T + Jvw w,   rpy+ = rpy + h w
+    // so one row of P+ times F (phase A, lane = row) and F' times one column of PF (phase B, lane = column;
+    // the vector tv rides along as a 14th column) are the same 54 multiply-adds on nine register operands,
+    // with every Jacobian word a broadcast load: half the flops of the dense products, a quarter of their
+    // shared-memory wavefronts, and thirteen independent accumulators per lane instead of three.
+    // Phases C and D: every lane owns a fixed set of matrix entries (compile-time trip counts, per-lane
+    // offsets hoisted out of the stage loop).  Returns false on a non-positive pivot.
+    //
+    // out[0..12] (v-ordering w0 w1 w2 T p0 p1 p2 v0 v1 v2 r0 r1 r2) = structured product of the 9-vector
+    // (xp, xv, xa) = (pos, vel, rpy parts) with F: out = F' x.
+    __device__ __forceinline__ static void ft_times(const T* __restrict__ jc, const T (&xp)[3], const T (&xv)[3], const T (&xa)[3], T (&out)[13])
+    {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            out[c] = (jc[JVW + c] * xv[0] + jc[JVW + 3 + c] * xv[1]) + (jc[JVW + 6 + c] * xv[2] + C::h * xa[c]);
+            out[4 + c] = xp[c];
+            out[7 + c] = ((jc[JPV + c] * xp[0] + jc[JPV + 3 + c] * xp[1]) + jc[JPV + 6 + c] * xp[2]) +
+                         ((jc[JVV + c] * xv[0] + jc[JVV + 3 + c] * xv[1]) + jc[JVV + 6 + c] * xv[2]);
+            out[10 + c] = (((jc[JPR + c] * xp[0] + jc[JPR + 3 + c] * xp[1]) + jc[JPR + 6 + c] * xp[2]) +
+                           ((jc[JVR + c] * xv[0] + jc[JVR + 3 + c] * xv[1]) + jc[JVR + 6 + c] * xv[2])) + xa[c];
+        }
+        out[3] = ((jc[JPT] * xp[0] + jc[JPT + 1] * xp[1]) + jc[JPT + 2] * xp[2]) +
+                 ((jc[JVT] * xv[0] + jc[JVT + 1] * xv[1]) + jc[JVT + 2] * xv[2]);
     }
 
     __device__ bool riccati_backward()
     {
-        constexpr int FDS = L::FDS;
-        T* PN = sm + L::PN; T* FD = sm + L::FD; T* PF = sm + L::PF; T* GG = sm + L::GG;
+        T* PN = sm + L::PN; T* PF = sm + L::PF; T* GG = sm + L::GG;
         T* TV = sm + L::TV; T* QUU = sm + L::QUU; T* QUR = sm + L::QUR;
         T* QV = sm + L::QV; T* QXI = sm + L::QXI; T* YS = sm + L::YS; T* Y0 = sm + L::Y0;
         bool ok = true;
@@ -472,69 +480,57 @@ template <typename T, int N> struct Solver {
             poff[t] = (i < 9) ? (i == j ? 8 + i : (i < 3 ? 17 + i + j - 1 : -1))             // Phi_xx
                               : (i == j ? 4 + i - 9 : -1);                                   // Phi_qq
         }
-        const int fdd0 = fd_slot(lane), fdd1 = fd_slot(lane + 32 < NJC ? lane + 32 : NJC - 1);
-        const bool has1 = lane + 32 < NJC;
-        // constant pattern of F (written once per sweep): zeros, identities, h
-        for (int e = lane; e < 9 * FDS; e += 32) FD[e] = T(0);
-        __syncwarp();
-        if (lane < 3) {
-            FD[lane * FDS + 4 + lane] = T(1);
-            FD[(6 + lane) * FDS + 10 + lane] = T(1);
-            FD[(6 + lane) * FDS + lane] = C::h;
-        }
-        {
-            const T* jcn = JC + (N - 2) * NJC;
-            FD[fdd0] = jcn[lane];
-            if (has1) FD[fdd1] = jcn[lane + 32];
-        }
-        __syncwarp();
         for (int k = N - 1; k >= 0; k--) {
             const bool nx = (k < N - 1);
             const T* phi = PHID + k * L::PHI_S;
             const T* gk = G + k * NZ;
             if (nx) {
-                // ---- phase A ------------------------------------------------------------------
-                const T* dk = D + k * NXI;
+                const T* jc = JC + k * NJC;
+                // ---- phase A: lane = row of P+ (xi-ordering) ----------------------------------
+                if (lane < NXI) {
+                    const T* pr = PN + lane * 13;
+                    const T xp[3] = {pr[0], pr[1], pr[2]}, xv[3] = {pr[3], pr[4], pr[5]}, xa[3] = {pr[6], pr[7], pr[8]};
+                    T out[13];
+                    ft_times(jc, xp, xv, xa, out);
+                    T* pf = PF + lane * 13;
 #pragma unroll
-                for (int t = 0; t < 6; t++) {
-                    const int e = lane + 32 * t;
-                    if (e < 169) {
-                        const int i = e / 13, j = e - 13 * i;
-                        PF[e] = dot3<T, 9, 1, FDS>(PN + i * 13, FD + j, T(0));
-                    } else if (e < 182) {
-                        const int i = e - 169;
-                        TV[i] = dot3<T, 13, 1, 1>(PN + i * 13, dk, P[(k + 1) * NXI + i]);
-                    }
+                    for (int c = 0; c < 13; c++) pf[c] = out[c];
+                    const T* dk = D + k * NXI;
+                    const T c0 = (((P[(k + 1) * NXI + lane] + xp[0] * dk[0]) + xv[0] * dk[3]) + xa[0] * dk[6]) + (pr[9] * dk[9] + pr[12] * dk[12]);
+                    const T c1 = ((xp[1] * dk[1] + xv[1] * dk[4]) + xa[1] * dk[7]) + pr[10] * dk[10];
+                    const T c2 = ((xp[2] * dk[2] + xv[2] * dk[5]) + xa[2] * dk[8]) + pr[11] * dk[11];
+                    TV[lane] = (c0 + c1) + c2;
                 }
                 __syncwarp();
-                // ---- phase B ------------------------------------------------------------------
+                // ---- phase B: lane = column of PF (v-ordering); lane 13 = the vector tv ----------
+                if (lane < 14) {
+                    const T* col = lane < 13 ? PF + lane : TV;
+                    const int cs = lane < 13 ? 13 : 1;
+                    const T xp[3] = {col[0], col[cs], col[2 * cs]}, xv[3] = {col[3 * cs], col[4 * cs], col[5 * cs]};
+                    const T xa[3] = {col[6 * cs], col[7 * cs], col[8 * cs]};
+                    T g[13];
+                    ft_times(jc, xp, xv, xa, g);
+                    if (lane < 4) {                                // column of Q_uu and of Q_xu = Q_ux'
+                        const int j = lane;
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int e = lane + 32 * t;
-                    if (t < 3 && e < 91) {
-                        const int i = ti[t], j = tj[t];            // v-ordering (u0..3, x0..8), i >= j
-                        T acc = dot3<T, 9, FDS, 13>(FD + i, PF + j, T(0));
-                        if (i < 4) {                               // Q_uu (then j < 4 too)
-                            acc += PN[(9 + i) * 13 + 9 + j] + PF[(9 + i) * 13 + j] + PF[(9 + j) * 13 + i];
+                        for (int i = 0; i < 4; i++) {
+                            T acc = g[i] + (PN[(9 + i) * 13 + 9 + j] + (PF[(9 + i) * 13 + j] + PF[(9 + j) * 13 + i]));
                             if (i == j) acc += phi[i];
                             QUU[i * 4 + j] = acc;
-                            QUU[j * 4 + i] = acc;
-                        } else if (j < 4) {                        // Q_ux[a = j][x = i - 4]
-                            QUR[j * 13 + i - 4] = acc + PF[(9 + j) * 13 + i];
-                        } else {
-                            GG[i * 13 + j] = acc;                  // Q_xx (lower), consumed in phase D
                         }
-                    } else if (e >= 91 && e < 108) {               // q~: w < 4 -> q_u, else q_xi
-                        const int w = e - 91;
-                        T v;
-                        if (w < 13) {
-                            const T base = (w < 4) ? gk[w] + TV[9 + w] : gk[w + 4];
-                            v = dot3<T, 9, FDS, 1>(FD + w, TV, base);
-                        } else {
-                            v = gk[w - 9];
-                        }
-                        if (w < 4) QV[w] = v; else QXI[w - 4] = v;
+#pragma unroll
+                        for (int i = 4; i < 13; i++) QUR[j * 13 + i - 4] = g[i] + PF[(9 + j) * 13 + i];
+                    } else if (lane < 13) {                        // column of Q_xx (phase D reads the lower triangle)
+#pragma unroll
+                        for (int i = 4; i < 13; i++) GG[i * 13 + lane] = g[i];
+                    } else {                                       // q~ = g + F' tv (+ the q+ = u part of tv)
+#pragma unroll
+                        for (int w = 0; w < 4; w++) QV[w] = g[w] + (gk[w] + TV[9 + w]);
+#pragma unroll
+                        for (int w = 4; w < 13; w++) QXI[w - 4] = g[w] + gk[w + 4];
                     }
+                } else if (lane >= 16 && lane < 20) {
+                    QXI[9 + lane - 16] = gk[4 + lane - 16];
                 }
                 if (lane < 16) QUR[(lane >> 2) * 13 + 9 + (lane & 3)] = ((lane >> 2) == (lane & 3)) ? phi[20] : T(0);
             } else {
@@ -586,11 +582,6 @@ template <typename T, int N> struct Solver {
                     const int i = e - 91;
                     P[k * NXI + i] = QXI[i] - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
                 }
-            }
-            if (k >= 1 && k <= N - 2) {                            // F of the next stage to be processed (k - 1)
-                const T* jcn = JC + (k - 1) * NJC;
-                FD[fdd0] = jcn[lane];
-                if (has1) FD[fdd1] = jcn[lane + 32];
             }
             __syncwarp();
             if (fac_out) {   // factor of stage k: P_k (91 words, PSYM layout) -> P region; [K_k 52 | Quu^-1 packed lower 10 | J_k 51] -> KQJ region
