@@ -28,7 +28,7 @@ class EllipsoidConsts(ctypes.Structure):
 EXPORTS = [
     "nmpc_default_opts", "nmpc_default_opts_f32", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
     "nmpc_smem_bytes", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
-    "nmpc_solve_batch_ex_f64",
+    "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64",
     "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_model_eval_host_f64",
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",

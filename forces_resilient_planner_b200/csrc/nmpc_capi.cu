@@ -77,7 +77,7 @@ template <typename T>
 int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr, const T* rows,
                  const int* nrows, int variant, const nmpc_opts* opts, T* z_out, int* info_int,
                  T* info_real, void* stream, T* y_out = nullptr, T* zl_out = nullptr, T* zu_out = nullptr,
-                 T* lc_out = nullptr)
+                 T* lc_out = nullptr, const int* order = nullptr)
 {
     if (B < 0 || mcap < 0 || mcap > 32 || (variant != 0 && variant != 1))
         return fail(NMPC_ERR_ARG, "bad argument: B=%d mcap=%d variant=%d", B, mcap, variant);
@@ -87,7 +87,7 @@ int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* h
         return fail(NMPC_ERR_ARG, "null pointer argument");
     nmpc::Params<T> prm;
     prm.B = B; prm.mcap = mcap; prm.variant = variant;
-    prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows;
+    prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order;
     prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
     nmpc_opts o;
@@ -397,6 +397,13 @@ int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double* xinit, const d
 {
     return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
                                 cuda_stream, y_out, zl_out, zu_out, lc_out);
+}
+int nmpc_solve_batch_ordered_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                                 const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
+                                 int* info_int, double* info_real, const int* order, void* cuda_stream)
+{
+    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
+                                cuda_stream, nullptr, nullptr, nullptr, nullptr, order);
 }
 int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                               const double* rows, const int* nrows, int variant, const nmpc_opts* opts,

@@ -41,6 +41,7 @@ template <typename T> struct Params {
     const T* hdr;      // [B][N][10]
     const T* rows;     // [B][N][mcap][4]
     const int* nrows;  // [B][N]
+    const int* order;  // [B] or nullptr: CTA i solves problem order[i] (launch order = scheduling order)
     T* z_out;          // [B][N][17]
     int* info_int;     // [B][4]  exitflag, iterations, backtracks, reserved
     T* info_real;      // [B][8]  res_eq res_ineq rsnorm rcompnorm pobj mu alpha_p alpha_d
@@ -790,8 +791,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     using C = Const<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const int b = blockIdx.x;
-    if (b >= prm.B) return;
+    if ((int)blockIdx.x >= prm.B) return;
+    const int b = prm.order ? prm.order[blockIdx.x] : (int)blockIdx.x;
     const int mcap = prm.mcap;
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);

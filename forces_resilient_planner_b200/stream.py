@@ -29,7 +29,7 @@ from .solver import _check
 
 class RecedingHorizonStream:
     def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True,
-                 wrap_yaw: bool = False, dynamic_ellipsoids: bool = False):
+                 wrap_yaw: bool = False, dynamic_ellipsoids: bool = False, longest_first: bool = True):
         import torch
         self.torch = torch
         self.dev = torch.device(device)
@@ -67,6 +67,11 @@ class RecedingHorizonStream:
         # ego ellipsoid; the cold start propagates along the cold guess, as the reference does after
         # initMPCOutput (:363-364).
         self.dynamic_ellipsoids = dynamic_ellipsoids
+        # True: warm solves are launched longest-first, ranked by the previous replan's iteration counts (failed
+        # agents, which restart cold, first).  CTAs start in index order, so the agents that spill into the
+        # second wave (1024 agents > 148 x 6 resident warps) are the quick ones and the launch ends sooner.
+        self.longest_first = longest_first
+        self.order = torch.arange(self.B, dtype=torch.int32, device=self.dev)
         self.cycle = 0
 
     # -- the three launches of a replan, all on `stream` ---------------------------------------------
@@ -86,10 +91,19 @@ class RecedingHorizonStream:
                   self.poly_m.data_ptr(), self.poly_idx.data_ptr(), w, hdr.data_ptr(), rows.data_ptr(),
                   nrows.data_ptr(), stream.cuda_stream))
         o = self.opts_warm if warm else self.opts_cold
-        _check(self.lib.nmpc_solve_batch_f64(self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(),
-                                             hdr.data_ptr(), rows.data_ptr(), nrows.data_ptr(), 0, ctypes.byref(o),
-                                             self.z.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr(),
-                                             ctypes.c_void_p(stream.cuda_stream)))
+        order = None
+        if warm and self.longest_first:
+            with torch.cuda.stream(stream):
+                key = self.info_int[:, 1] + 1000 * (self.info_int[:, 0] != 1).int()
+                self.order.copy_(torch.argsort(key, descending=True, stable=True))
+            order = self.order.data_ptr()
+        fn = self.lib.nmpc_solve_batch_ordered_f64
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + \
+            [ctypes.c_void_p] * 5
+        _check(fn(self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(), hdr.data_ptr(), rows.data_ptr(),
+                  nrows.data_ptr(), 0, ctypes.byref(o), self.z.data_ptr(), self.info_int.data_ptr(),
+                  self.info_real.data_ptr(), order, ctypes.c_void_p(stream.cuda_stream)))
 
     def replan(self, ref_pos: np.ndarray, ref_yaw: np.ndarray, ext_acc: np.ndarray):
         """One cycle.  Host arrays in (refs of this cycle), host arrays out (first command, flags).

@@ -91,6 +91,15 @@ int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double *xinit, const d
                             double *y_out, double *zl_out, double *zu_out, double *lc_out,
                             void *cuda_stream);
 
+/* as nmpc_solve_batch_f64 with an explicit scheduling order: CTA i solves problem order[i] (a device
+ * permutation of 0..B-1; NULL = natural order).  The hardware starts CTAs in index order, so a
+ * longest-first order (e.g. by the previous replan's iteration counts in a receding-horizon stream)
+ * shortens the tail of the launch; results are written at the problems' own indices.            */
+int nmpc_solve_batch_ordered_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                                 const double *hdr, const double *rows, const int *nrows,
+                                 int variant, const nmpc_opts *opts, double *z_out, int *info_int,
+                                 double *info_real, const int *order, void *cuda_stream);
+
 /* ---- host-pointer API: H2D copies, solve, D2H copies, synchronous --------------------------- */
 int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double *xinit, const double *z0,
                               const double *hdr, const double *rows, const int *nrows, int variant,

@@ -283,6 +283,28 @@ def test_stream_with_propagated_ellipsoids_matches_cpu_closed_loop():
     assert np.all(rows[:, 5:, :6, 3] < static[:, 4:] - 0.05)
 
 
+def test_scheduling_order_does_not_change_results():
+    """nmpc_solve_batch_ordered_f64: CTA i solves problem order[i]; outputs stay at the problems' own indices."""
+    import torch
+    b = W.config3(300)
+    db = S.DeviceBatch(b, np.float64, "cuda:0")
+    S.solve_device(db)
+    ref = db.result()
+    lib = _lib.load()
+    fn = lib.nmpc_solve_batch_ordered_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + [ctypes.c_void_p] * 5
+    order = torch.from_numpy(np.random.default_rng(3).permutation(b.B).astype(np.int32)).cuda()
+    d = db.d
+    z = torch.zeros_like(db.z); ii = torch.zeros_like(db.info_int); ir = torch.zeros_like(db.info_real)
+    o = _lib.default_opts()
+    rc = fn(b.B, b.N, b.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(), d["rows"].data_ptr(),
+            d["nrows"].data_ptr(), 0, ctypes.byref(o), z.data_ptr(), ii.data_ptr(), ir.data_ptr(), order.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert np.array_equal(z.cpu().numpy(), ref.z) and np.array_equal(ii.cpu().numpy()[:, 1], ref.it)
+
+
 def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows():
     """The reference layout allows 30 rows per stage; DecompROS polytopes can also leave zero rows in
     the middle once tightened rows are dropped upstream.  The shim compacts them; the result must
