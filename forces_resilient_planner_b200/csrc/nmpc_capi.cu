@@ -19,6 +19,7 @@
 #include "../../include/FORCESNLPsolver_normal.h"
 #include "../../include/nmpc_b200.h"
 #include "nmpc_backsolve.cuh"
+#include "nmpc_corridor.cuh"
 #include "nmpc_ellipsoid.cuh"
 #include "nmpc_ipm.cuh"
 #include "nmpc_prep.cuh"
@@ -451,6 +452,32 @@ int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double* ref
                        weights5[0], weights5[1], weights5[2], weights5[3], weights5[4], hdr, rows, nrows};
     const int n = B * N;
     nmpc::pack_params_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nmpc_select_corridors_f64(int B, int N, int M, int P, int R, const double* cloud, long long cloud_stride,
+                              const int* cloud_n, const double* ref_pos, const double* ref_yaw, const double* ellipsoid,
+                              const double* bbox3, double* poly_A, double* poly_b, int* poly_m, int* poly_idx, int* n_poly,
+                              int* overflow, void* stream)
+{
+    if (B < 0 || N <= 0 || M < 0 || P <= 0 || R < 7 || (cloud_stride != 0 && cloud_stride < 3LL * M))
+        return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d M=%d P=%d R=%d stride=%lld", B, N, M, P, R, cloud_stride);
+    if (B == 0) return 0;
+    if ((M > 0 && !cloud) || !cloud_n || !ref_pos || !ref_yaw || !ellipsoid || !poly_A || !poly_b || !poly_m || !poly_idx ||
+        !n_poly || !overflow)
+        return fail(NMPC_ERR_ARG, "null pointer argument");
+    const size_t smem = ((size_t)(M + 15) & ~(size_t)15) + (size_t)R * 4 * sizeof(double);
+    if (smem > 200 * 1024) return fail(NMPC_ERR_ARG, "cloud too large for the per-agent flag array: M=%d", M);
+    static thread_local size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::corridor_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    nmpc::CorridorParams q{B, N, M, P, R, cloud, cloud_stride, cloud_n, ref_pos, ref_yaw, ellipsoid,
+                           bbox3 ? bbox3[0] : 2.0, bbox3 ? bbox3[1] : 2.0, bbox3 ? bbox3[2] : 1.0,
+                           poly_A, poly_b, poly_m, poly_idx, n_poly, overflow};
+    nmpc::corridor_select_kernel<<<B, nmpc::COR_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

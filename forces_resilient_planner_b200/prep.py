@@ -98,3 +98,37 @@ def propagate_ellipsoids(z, consts=None, out=None, stream=None):
     with torch.cuda.device(z.device):
         _check(fn(B, N, z.data_ptr(), ctypes.byref(c), out.data_ptr(), st.cuda_stream))
     return out
+
+
+def select_corridors(cloud, cloud_n, ref_pos, ref_yaw, ellipsoid, max_polys=8, max_rows=30, bbox=(2.0, 2.0, 1.0),
+                     stream=None):
+    """Corridor generation + per-stage polytope selection on the device (getSikangConst / setFORCESParams,
+    nmpc_solver.cpp:288-332, 493-516; DecompROS EllipsoidDecomp::dilate).
+
+    cloud [B,M,3] per agent or [M,3] shared (cuda, float64), cloud_n [B] / [1] (int32), ref_pos [B,N,3],
+    ref_yaw [B,N], ellipsoid [B,N,9]  ->  poly_A [B,P,R,3], poly_b [B,P,R], poly_m [B,P], poly_idx [B,N],
+    n_poly [B], overflow [B]."""
+    import torch
+    lib = _lib.load()
+    B, N, _ = ref_pos.shape
+    shared = cloud.dim() == 2
+    M = cloud.shape[0] if shared else cloud.shape[1]
+    dev = ref_pos.device
+    P, R = int(max_polys), int(max_rows)
+    poly_A = torch.zeros((B, P, R, 3), dtype=torch.float64, device=dev)      # unused polytope slots stay zero
+    poly_b = torch.zeros((B, P, R), dtype=torch.float64, device=dev)
+    poly_m = torch.empty((B, P), dtype=torch.int32, device=dev)
+    poly_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
+    n_poly = torch.empty((B,), dtype=torch.int32, device=dev)
+    overflow = torch.empty((B,), dtype=torch.int32, device=dev)
+    fn = lib.nmpc_select_corridors_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 4 + \
+        [ctypes.POINTER(ctypes.c_double)] + [ctypes.c_void_p] * 7
+    bb = (ctypes.c_double * 3)(*[float(x) for x in bbox])
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _check(fn(B, N, M, P, R, cloud.data_ptr(), 0 if shared else 3 * M, cloud_n.data_ptr(), ref_pos.data_ptr(),
+                  ref_yaw.data_ptr(), ellipsoid.data_ptr(), bb, poly_A.data_ptr(), poly_b.data_ptr(), poly_m.data_ptr(),
+                  poly_idx.data_ptr(), n_poly.data_ptr(), overflow.data_ptr(), st.cuda_stream))
+    return poly_A, poly_b, poly_m, poly_idx, n_poly, overflow

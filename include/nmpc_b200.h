@@ -173,6 +173,26 @@ void nmpc_default_ellipsoid_consts(nmpc_ellipsoid_consts *c);
 int nmpc_propagate_ellipsoids_f64(int B, int N, const double *z, const nmpc_ellipsoid_consts *consts,
                                   double *ellipsoid, void *cuda_stream);
 
+/* ---- corridor generation + per-stage polytope selection, device-resident --
+ * Batched form of the poly_indices / poly_constraints_ part of NMPCSolver::setFORCESParams with
+ * getSikangConst (plan_manage/src/nmpc_solver.cpp:288-332, 493-516) and of the DecompROS routines it
+ * drives (ThirdParty/DecompROS/decomp_ros_utils/include/decomp_util/{ellipsoid_decomp,line_segment,
+ * decomp_base}.h, decomp_geometry/{ellipsoid,polyhedron}.h): per agent, walk the stages; keep the last
+ * polytope while the reference point inflated by 1.1 ||E_i a_j|| is inside it, otherwise dilate a new
+ * one (ellipsoid fit + half-space carving over the obstacle cloud + local box) around the 0.1 m seed
+ * segment along the yaw reference.
+ *   cloud [B][M][3] obstacle points per agent (cloud_stride = doubles between agents, 3*M; 0 = one cloud
+ *   shared by all, then cloud_n has one entry), cloud_n live points, ref_pos [B][N][3], ref_yaw [B][N],
+ *   ellipsoid [B][N][9] (from nmpc_propagate_ellipsoids_f64), bbox3 (HOST, NULL = {2, 2, 1}, :323)
+ *   -> poly_A [B][P][R][3], poly_b [B][P][R], poly_m [B][P], poly_idx [B][N]  (the inputs of
+ *      nmpc_pack_params_f64 with M := R), n_poly [B], overflow [B] (bit 0: a polytope had more than R
+ *      rows, bit 1: more than P polytopes were needed; 0 = exact).  R >= 7.  Device pointers.        */
+int nmpc_select_corridors_f64(int B, int N, int M, int P, int R, const double *cloud,
+                              long long cloud_stride, const int *cloud_n, const double *ref_pos,
+                              const double *ref_yaw, const double *ellipsoid, const double *bbox3,
+                              double *poly_A, double *poly_b, int *poly_m, int *poly_idx, int *n_poly,
+                              int *overflow, void *cuda_stream);
+
 /* ---- measured CUDA-core FMA peak (TFLOP/s) of the current device, elem_size 8 (fp64) or 4 (fp32):
  * the roofline denominator for the fused solver kernel, which is FMA-issue/latency bound, not
  * HBM bound (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).                       */

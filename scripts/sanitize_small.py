@@ -17,3 +17,6 @@ path = t(np.cumsum(rng.normal(scale=0.05, size=(7, 30, 3)), axis=1)); size = tor
 rp, ry, far = prep.sample_reference(path, size, t(rng.uniform(0, 1, 7)), t(rng.uniform(-3, 3, 7)), 20, 0.05, pos1=t(rng.normal(size=(7, 3))))
 E = prep.propagate_ellipsoids(t(g.z[:3, :20].astype(np.float64).copy()))
 torch.cuda.synchronize(); print("sample + ellipsoids ok", float(E.abs().max()))
+cloud = t(rng.uniform([-1, -2, 0], [5, 2, 2], (200, 3))); ref = np.zeros((3, 20, 3)); ref[:, :, 0] = 0.2 * np.arange(20); ref[:, :, 2] = 1.0
+out = prep.select_corridors(cloud, torch.tensor([200], dtype=torch.int32).cuda(), t(ref), t(np.zeros((3, 20))), E, max_polys=20, max_rows=30)
+torch.cuda.synchronize(); print("corridors ok", out[4].tolist(), out[5].tolist())

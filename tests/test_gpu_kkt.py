@@ -161,3 +161,49 @@ def test_ellipsoid_propagation_matches_the_literal_restatement():
     E20 = EN.propagate_batch(z[:5], EN.EllipsoidConsts(mass=0.74, ext_noise_bound=0.3))
     assert np.max(np.abs(E2 - E20)) < 1e-11 * np.max(np.abs(E20))
     assert np.all(np.trace(E2, axis1=-2, axis2=-1)[:, 1:] < np.trace(E[:5], axis1=-2, axis2=-1)[:, 1:])   # smaller noise bound
+
+
+def test_corridor_selection_matches_the_decomp_restatement():
+    """Rank 4 of SURVEY §8f: getSikangConst + EllipsoidDecomp::dilate per agent on the device vs the loop
+    restatement (oracle/corridor_np.py): same polytopes (rows in the same order), same stage -> polytope map."""
+    import torch
+    from oracle import corridor_np as CN
+    from test_prep_host import _scene
+    rng = np.random.default_rng(7)
+    B, N, M, P, R = 12, 20, 512, 20, 40
+    refs, yaws, clouds, cn = [], [], np.zeros((B, M, 3)), np.zeros(B, np.int32)
+    for a in range(B):
+        ref, yaw, cloud = _scene(rng, n_pts=rng.integers(0, 450) if a else 0, clear=rng.uniform(0.02, 0.5))
+        ref = ref + rng.normal(scale=0.3, size=3)          # off the centre of the clear tube
+        if a == 3:                                   # obstacles inside the 5 cm seed sphere of stage 0
+            cloud = np.concatenate([cloud, ref[0] + np.array([[0.05, 0.03, 0.0], [0.06, -0.02, 0.02]])])
+        refs.append(ref); yaws.append(yaw); cn[a] = len(cloud); clouds[a, :len(cloud)] = cloud
+    refs, yaws = np.stack(refs), np.stack(yaws)
+    E = np.tile(np.diag([0.27, 0.27, 0.0425]).reshape(1, 1, 3, 3), (B, N, 1, 1)) * (1 + 0.04 * np.arange(N))[None, :, None, None]
+    pa, pb, pm, pidx, npoly, ovf = prep.select_corridors(_t(clouds), torch.from_numpy(cn).cuda(), _t(refs), _t(yaws),
+                                                         _t(E.reshape(B, N, 9)), max_polys=P, max_rows=R)
+    pa, pb, pm, pidx, npoly, ovf = (x.cpu().numpy() for x in (pa, pb, pm, pidx, npoly, ovf))
+    assert np.all(ovf == 0)
+    total = 0
+    for a in range(B):
+        polys, idx = CN.select_corridors(refs[a], yaws[a], E[a], clouds[a, :cn[a]])
+        assert npoly[a] == len(polys) and np.array_equal(pidx[a], idx), a
+        for k, (A, b) in enumerate(polys):
+            assert pm[a, k] == len(b), (a, k)
+            assert np.max(np.abs(pa[a, k, :len(b)] - A)) < 1e-9 and np.max(np.abs(pb[a, k, :len(b)] - b)) < 1e-9, (a, k)
+            assert np.all(pa[a, k, len(b):] == 0)
+            total += 1
+    assert total > 2 * B
+    # one cloud shared by all agents gives the same answer as B copies of it
+    shared = clouds[5, :cn[5]].copy()
+    out_s = prep.select_corridors(_t(shared), torch.tensor([len(shared)], dtype=torch.int32).cuda(), _t(refs), _t(yaws),
+                                  _t(E.reshape(B, N, 9)), max_polys=P, max_rows=R)
+    rep = np.zeros((B, M, 3)); rep[:, :len(shared)] = shared
+    out_r = prep.select_corridors(_t(rep), torch.full((B,), len(shared), dtype=torch.int32).cuda(), _t(refs), _t(yaws),
+                                  _t(E.reshape(B, N, 9)), max_polys=P, max_rows=R)
+    for x, y in zip(out_s, out_r):
+        assert torch.equal(x, y)
+    # the polytopes feed pack_params unchanged
+    hdr, rows, nrows = prep.pack_params(_t(refs), _t(yaws), _t(np.zeros((B, 3))), _t(E.reshape(B, N, 9)), out_r[0], out_r[1],
+                                        out_r[2], out_r[3], (7.0, 1.0, 80.0, 12.0, 0.5), 30)
+    assert int(nrows.max()) <= 30 and int(nrows.min()) >= 6

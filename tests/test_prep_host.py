@@ -109,3 +109,46 @@ def test_ellipsoid_restatement_properties():
     assert np.max(np.abs(X - Xq)) < 1e-12 * np.max(np.abs(X))
     # closed loop used by the reference is stable at hover (otherwise the Sylvester equation could be singular)
     assert np.max(np.linalg.eigvals(Phi).real) < 0
+
+
+def _scene(rng, n_pts=300, clear=0.35):
+    """A straight reference through random clutter, with a clear tube around it."""
+    N = 20
+    ref = np.zeros((N, 3)); ref[:, 0] = 0.25 * np.arange(N); ref[:, 1] = 0.3 * np.sin(0.3 * np.arange(N)); ref[:, 2] = 1.0
+    yaw = np.arctan2(np.gradient(ref[:, 1]), np.gradient(ref[:, 0]))
+    pts = rng.uniform([-1.5, -3.0, 0.0], [6.5, 3.0, 2.2], (n_pts, 3))
+    dist = np.min(np.linalg.norm(pts[:, None, :] - ref[None], axis=2), axis=1)
+    return ref, yaw, pts[dist > clear]
+
+
+def test_corridor_restatement_properties():
+    """oracle/corridor_np.py against facts that do not depend on its own code path."""
+    from oracle import corridor_np as CN
+    p1 = np.array([1.0, 2.0, 1.0]); p2 = p1 + np.array([0.1, 0.0, 0.0])
+    # no obstacles: only the local box, 2 m beyond each end, 2 m to the sides, 1 m up and down
+    A, b = CN.dilate_segment(p1, p2, np.zeros((0, 3)))
+    assert A.shape == (6, 3) and np.allclose(np.linalg.norm(A, axis=1), 1.0)
+    ext = {tuple(np.round(a, 12)): bb for a, bb in zip(A, b)}
+    assert np.isclose(ext[(1.0, 0.0, 0.0)], 1.1 + 2.0) and np.isclose(ext[(-1.0, 0.0, 0.0)], -(1.0 - 2.0))
+    assert np.isclose(ext[(0.0, 0.0, 1.0)], 2.0) and np.isclose(ext[(0.0, 0.0, -1.0)], 0.0)
+    # one obstacle: the seed ellipsoid is a sphere, so the plane is tangent to the sphere's metric at the point
+    pt = np.array([2.0, 2.5, 1.2])
+    A, b = CN.dilate_segment(p1, p2, pt[None])
+    n = (pt - (p1 + p2) / 2); n /= np.linalg.norm(n)
+    assert A.shape == (7, 3) and np.allclose(A[0], n) and np.isclose(b[0], n @ pt)
+    # a second point hidden behind the first plane produces no plane of its own; one in front does
+    A2, _ = CN.dilate_segment(p1, p2, np.stack([pt, pt + 0.5 * n, np.array([1.05, 1.2, 1.0])]))
+    assert A2.shape == (8, 3)
+    # the safe-corridor property on clutter: midpoint strictly inside, every obstacle of the box on or outside a face
+    rng = np.random.default_rng(0)
+    ref, yaw, cloud = _scene(rng)
+    polys, idx = CN.select_corridors(ref, yaw, np.tile(np.diag([0.27, 0.27, 0.0425]), (20, 1, 1)), cloud)
+    assert len(polys) >= 2 and np.all(np.diff(idx) >= 0) and idx[0] == 0 and idx[-1] == len(polys) - 1
+    for k, (A, b) in enumerate(polys):
+        first = int(np.argmax(idx == k))
+        mid = ref[first] + 0.05 * np.array([np.cos(yaw[first]), np.sin(yaw[first]), 0.0])
+        assert np.all(A @ mid - b < 0)
+        assert np.all(np.max(cloud @ A.T - b, axis=1) > -1e-9)
+    # an obstacle within the 5 cm seed sphere shrinks the ellipsoid instead of being swallowed
+    C, d = CN.find_ellipsoid(p1, p2, [np.array([1.05, 2.03, 1.0])])
+    assert np.linalg.norm(np.linalg.inv(C) @ (np.array([1.05, 2.03, 1.0]) - d)) >= 1 - 1e-9
