@@ -164,3 +164,67 @@ def synthetic_refs(batch: W.Batch, step: int, rng: np.random.Generator, ext_acc:
     yaw = np.repeat(hdr[:, -1:, 9], batch.N, axis=1) if step > 0 else hdr[:, :, 9].copy()
     ext = np.clip(ext_acc + rng.normal(0.0, 0.1, ext_acc.shape), -2.5, 2.5) if step > 0 else ext_acc
     return np.ascontiguousarray(ref), np.ascontiguousarray(yaw), np.ascontiguousarray(ext)
+
+
+class PlannerPipeline:
+    """One replan of the reference's `setFORCESParams` + `solveNormal` for B agents, device-resident end to end
+    (SURVEY.md §8f rank 1-4 + the solve):
+
+        shift warm start        nmpc_shift_warm_start_f64      nmpc_solver.cpp:531-543, forces_normal.cpp:62-97
+        disturbance ellipsoids  nmpc_propagate_ellipsoids_f64  :484-521, 567-699      (along the previous plan)
+        references + yaw        nmpc_sample_reference_f64      :109-142, 834-862      (front-end polyline at Ts)
+        corridors               nmpc_select_corridors_f64      :288-332, DecompROS    (obstacle cloud -> polytopes)
+        parameters              nmpc_pack_params_f64           forces_normal.cpp:100-136
+        solve                   nmpc_solve_batch_ordered_f64   FORCESNLPsolver_normal_solve
+
+    The front end stays on the host: it supplies the polyline `kino_path` (sampled at Ts) and the obstacle `cloud`.
+    """
+
+    def __init__(self, xinit, kino_path, kino_size, cloud, cloud_n, device="cuda:0", mcap=30, max_polys=20,
+                 weights=(7.0, 1.0, 80.0, 12.0, 0.5), Ts=0.05, N=20, mu0_warm=0.1):
+        import torch
+        self.torch = torch
+        self.dev = torch.device(device)
+        t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.dev)
+        self.B, self.N, self.mcap, self.P, self.Ts = xinit.shape[0], N, mcap, max_polys, Ts
+        self.kino_path, self.kino_size = t(kino_path), t(kino_size, torch.int32)
+        self.cloud, self.cloud_n = t(cloud), t(cloud_n, torch.int32)
+        self.weights = weights
+        z0 = W.cold_start(xinit, N)                                   # initMPCOutput (nmpc_solver.cpp:265-286)
+        self.xinit, self.z0 = t(xinit), t(z0)
+        self.z = self.z0.clone()                                      # "previous plan" of the first cycle = the cold guess
+        self.info_int = torch.zeros((self.B, 4), dtype=torch.int32, device=self.dev)
+        self.info_real = torch.zeros((self.B, 8), dtype=torch.float64, device=self.dev)
+        self.opts_cold, self.opts_warm = _lib.default_opts(), _lib.default_opts(mu0=mu0_warm)
+        self.lib = _lib.load()
+        self.cycle = 0
+        self.last = {}
+
+    def replan(self, ext_acc: np.ndarray, t_off: np.ndarray):
+        """ext_acc [B,3], t_off [B] (= mpc_start_time_ - kino_start_time_) on the host -> (commands, flags, iterations)."""
+        torch = self.torch
+        st = torch.cuda.current_stream(self.dev)
+        warm = self.cycle > 0
+        ext = torch.from_numpy(np.ascontiguousarray(ext_acc)).to(self.dev)
+        toff = torch.from_numpy(np.ascontiguousarray(t_off)).to(self.dev)
+        prev = self.z                                                  # mpc_output_ of the last cycle (cold guess at first)
+        if warm:
+            prep.shift_warm_start(prev, self.xinit, self.z0, wrap_yaw=True, stream=st)
+        E = prep.propagate_ellipsoids(prev, stream=st)
+        last_yaw = prev[:, 1, 16].contiguous(); pos1 = prev[:, 1, 8:11].contiguous()
+        ref_pos, ref_yaw, far = prep.sample_reference(self.kino_path, self.kino_size, toff, last_yaw, self.N, self.Ts,
+                                                      pos1=pos1, stream=st)
+        pA, pb, pm, pidx, npoly, ovf = prep.select_corridors(self.cloud, self.cloud_n, ref_pos, ref_yaw, E,
+                                                             max_polys=self.P, max_rows=self.mcap, stream=st)
+        hdr, rows, nrows = prep.pack_params(ref_pos, ref_yaw, ext, E, pA, pb, pm, pidx, self.weights, self.mcap, stream=st)
+        z_new = torch.empty_like(self.z)
+        o = self.opts_warm if warm else self.opts_cold
+        _check(self.lib.nmpc_solve_batch_f64(self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(),
+                                             hdr.data_ptr(), rows.data_ptr(), nrows.data_ptr(), 0, ctypes.byref(o),
+                                             z_new.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr(),
+                                             ctypes.c_void_p(st.cuda_stream)))
+        self.z = z_new
+        self.cycle += 1
+        self.last = dict(ellipsoid=E, ref_pos=ref_pos, ref_yaw=ref_yaw, hard_to_follow=far, poly_idx=pidx, n_poly=npoly,
+                         overflow=ovf, hdr=hdr, rows=rows, nrows=nrows)
+        return self.z[:, 0, 0:4].cpu().numpy(), self.info_int[:, 0].cpu().numpy(), self.info_int[:, 1].cpu().numpy()

@@ -283,6 +283,60 @@ def test_stream_with_propagated_ellipsoids_matches_cpu_closed_loop():
     assert np.all(rows[:, 5:, :6, 3] < static[:, 4:] - 0.05)
 
 
+def test_planner_pipeline_matches_cpu_twin():
+    """setFORCESParams + solveNormal for a few agents, every step on the device (shift, ellipsoids, references,
+    corridors from an obstacle cloud, packing, solve), against the same replans assembled from the CPU
+    restatements (oracle/prep_np.py, ellipsoid_np.py, corridor_np.py) and solved by the CPU oracle."""
+    from forces_resilient_planner_b200 import stream as ST
+    from oracle import corridor_np as CN, ellipsoid_np as EN
+    rng = np.random.default_rng(21)
+    B, N, P, Ts, mcap = 5, 20, 60, 0.05, 30
+    # front end: a gently curving 1 m/s polyline per agent through clutter with a clear tube, sampled at Ts
+    k = np.arange(P)
+    paths = np.zeros((B, P, 3)); clouds = np.zeros((B, 400, 3)); cn = np.zeros(B, np.int32)
+    for a in range(B):
+        head = rng.uniform(-np.pi, np.pi)
+        ang = head + 0.25 * np.sin(0.08 * k + rng.uniform(0, 6))
+        paths[a, :, 0] = np.cumsum(0.05 * np.cos(ang)); paths[a, :, 1] = np.cumsum(0.05 * np.sin(ang)); paths[a, :, 2] = 1.0 + 0.1 * a
+        pts = rng.uniform(paths[a].min(0) - [2.5, 2.5, 1.0], paths[a].max(0) + [2.5, 2.5, 1.0], (400, 3))
+        keep = pts[np.min(np.linalg.norm(pts[:, None] - paths[a][None], axis=2), axis=1) > 0.9]
+        cn[a] = len(keep); clouds[a, :len(keep)] = keep
+    size = np.full(B, P, np.int32)
+    xinit = np.zeros((B, 9)); xinit[:, 0:3] = paths[:, 0]; xinit[:, 8] = np.arctan2(paths[:, 5, 1] - paths[:, 0, 1], paths[:, 5, 0] - paths[:, 0, 0])
+    pipe = ST.PlannerPipeline(xinit, paths, size, clouds, cn, mcap=mcap, max_polys=20)
+    w5 = pipe.weights
+    prev = W.cold_start(xinit, N); x_c, z0_c = xinit.copy(), prev.copy()
+    ext = rng.uniform(-0.5, 0.5, (B, 3))
+    for cyc in range(4):
+        t_off = np.full(B, cyc * Ts) + rng.uniform(0, 0.01, B)
+        cmd, flag, it = pipe.replan(ext, t_off)
+        # ---- CPU twin ----
+        if cyc > 0:
+            prev_w = PN.wrap_yaw(prev)
+            x_c, z0_c = W.shift_warm_start(prev_w)
+        E = EN.propagate_batch(prev)
+        rp, ry, far = PN.sample_reference(paths, size, t_off, prev[:, 1, 16], N, Ts, pos1=prev[:, 1, 8:11])
+        pA = np.zeros((B, 20, mcap, 3)); pb = np.zeros((B, 20, mcap)); pm = np.zeros((B, 20), np.int32); pidx = np.zeros((B, N), np.int32)
+        for a in range(B):
+            polys, idx = CN.select_corridors(rp[a], ry[a], E[a], clouds[a, :cn[a]])
+            pidx[a] = idx
+            for q, (A, b) in enumerate(polys):
+                m = min(len(b), mcap); pA[a, q, :m] = A[:m]; pb[a, q, :m] = b[:m]; pm[a, q] = m
+        hdr, rows, nrows = PN.pack_params_reference(rp, ry, ext, E.reshape(B, N, 9), pA, pb, pm, pidx, w5, mcap)
+        L = pipe.last
+        assert np.max(np.abs(L["ref_pos"].cpu().numpy() - rp)) < 1e-12 and np.max(np.abs(L["ref_yaw"].cpu().numpy() - ry)) < 1e-11, cyc
+        assert np.array_equal(L["poly_idx"].cpu().numpy(), pidx) and np.all(L["overflow"].cpu().numpy() == 0), cyc
+        assert np.array_equal(L["nrows"].cpu().numpy(), nrows), cyc
+        assert np.max(np.abs(L["rows"].cpu().numpy() - rows)) < 1e-8 and np.max(np.abs(L["hdr"].cpu().numpy() - hdr)) < 1e-11, cyc
+        c = O.solve_batch(W.Batch(x_c, z0_c, hdr, rows, nrows, 0), opts=O.default_opts(mu0=1.0 if cyc == 0 else 0.1))
+        assert np.all(flag == 1) and np.all(c["flag"] == 1), (cyc, flag, c["flag"])
+        assert np.array_equal(it, c["it"]), cyc
+        assert np.max(np.abs(cmd - c["z"][:, 0, 0:4])) < 1e-6, cyc
+        prev = c["z"]
+    # the vehicles actually follow their paths
+    assert np.max(np.linalg.norm(prev[:, 1, 8:11] - rp[:, 0], axis=1)) < 0.3
+
+
 def test_scheduling_order_does_not_change_results():
     """nmpc_solve_batch_ordered_f64: CTA i solves problem order[i]; outputs stay at the problems' own indices."""
     import torch
