@@ -499,7 +499,14 @@ int nmpc_propagate_ellipsoids_f64(int B, int N, const double* z, const nmpc_elli
     if (!(c.mass > 0) || !(c.Ts > 0) || !(c.ext_noise_bound > 0) || !(c.epsilon > 0))
         return fail(NMPC_ERR_ARG, "bad ellipsoid constants");
     nmpc::EllipsoidParams q{B, N, z, ellipsoid, c.mass, c.drag, c.ego_r, c.ego_h, c.ext_noise_bound, c.epsilon, c.Ts};
-    nmpc::ellipsoid_propagate_kernel<<<(B + nmpc::ELL_WARPS - 1) / nmpc::ELL_WARPS, 32 * nmpc::ELL_WARPS, 0,
+    const size_t smem = nmpc::ellipsoid_smem_bytes(N);
+    if (smem > 200 * 1024) return fail(NMPC_ERR_ARG, "horizon too long for the ellipsoid kernel: N=%d", N);
+    static thread_local size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::ellipsoid_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    nmpc::ellipsoid_propagate_kernel<<<(B + nmpc::ELL_WARPS - 1) / nmpc::ELL_WARPS, 32 * nmpc::ELL_WARPS, smem,
                                        reinterpret_cast<cudaStream_t>(stream)>>>(q);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -24,8 +24,9 @@
 // One deliberate deviation, in both: the reference accumulates `temp += sqrt(X.trace())` into an
 // uninitialised double (:573, :597 -- undefined behaviour); here temp starts at 0.
 //
-// The stages are a recurrence (Q_init and Q2 carry over), so a warp walks its agent's horizon;
-// lanes split the matrix entries.
+// The stages are a recurrence (Q_init and Q2 carry over), so a warp walks its agent's horizon with the lanes
+// splitting the matrix entries; what does not take part in the recurrence is done for all stages at
+// once with one stage per lane: the linearisation scalars before the walk, the 3x3 square roots after it.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -48,7 +49,7 @@ __device__ const double ELL_KT[36] = {
 constexpr int ELL_K = 20;              // series terms: ||Phi t|| ~ 1.3, 1.3^20 / 20! ~ 1e-16
 constexpr int ELL_KP = ELL_K + 1;
 constexpr int ELL_Q = 12;              // Gauss-Legendre nodes on [0, t]: exact to degree 23 of the series product
-constexpr int ELL_WARPS = 3;           // agents per CTA (14.1 KB of shared memory each)
+constexpr int ELL_WARPS = 2;           // agents per CTA (14.1 KB + 312 N bytes of shared memory each)
 static_assert(ELL_KP % 3 == 0 && ELL_Q % 2 == 0, "unrolled accumulation chains");
 
 // nodes xi_q in (0, 1) and sqrt(weight_q / 2) of the 12-point Gauss-Legendre rule
@@ -103,20 +104,25 @@ __device__ __forceinline__ void sqrtm3_sym(const double q[9], double e[9])
         for (int j = 0; j < 3; j++) e[3 * i + j] = v[i][0] * l0 * v[j][0] + v[i][1] * l1 * v[j][1] + v[i][2] * l2 * v[j][2];
 }
 
+constexpr int ELL_SCW = 30;            // per-stage scalars: a[9] = At(3:6, 6:9) | RDR'[9] = At(3:6, 3:6) | bt[3] = Bt(3:6, 3) | Q1[9]
+constexpr int ELL_FIXED = 243 + 27 * ELL_KP + 27 * ELL_Q + 243 + ELL_KP * ELL_Q + 81 + ELL_KP + 1 + 32;   // doubles per warp besides the per-stage tables
+__host__ __device__ constexpr size_t ellipsoid_smem_bytes(int N) { return (size_t)ELL_WARPS * (ELL_FIXED + N * (ELL_SCW + 9)) * sizeof(double); }
+
 __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(const EllipsoidParams q)
 {
     // per warp: A = Phi t | Q_origin | Qd | U (3 x 9 x KP) | V (3 x 9 x Q) | X (3 x 81) | node powers sqrt(w_q/2) xi_q^j
-    // | first three rows of exp(A) (3 x 9) | row-series terms (2 x 27) | 1/k | scalars of the stage
+    // | first three rows of exp(A) (3 x 9) | row-series terms (2 x 27) | 1/k | scratch | per-stage scalars [N][30] | Q_i [N][9]
     constexpr int O_A = 0, O_QO = 81, O_TQ = 162, O_U = 243, O_V = O_U + 27 * ELL_KP, O_X = O_V + 27 * ELL_Q,
                   O_PW = O_X + 243, O_ER = O_PW + ELL_KP * ELL_Q, O_Y0 = O_ER + 27, O_Y1 = O_Y0 + 27, O_INV = O_Y1 + 27,
-                  O_SC = O_INV + ELL_KP + 1, O_END = O_SC + 32;
-    __shared__ double smem[ELL_WARPS][O_END];
+                  O_SC = O_INV + ELL_KP + 1, O_SCA = O_SC + 32;
+    static_assert(O_SCA == ELL_FIXED, "shared-memory plan");
+    extern __shared__ double ell_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * ELL_WARPS + wid;
     if (b >= q.B) return;
-    double* S = smem[wid];
+    double* S = ell_smem + (size_t)wid * (ELL_FIXED + q.N * (ELL_SCW + 9));
     double *A = S + O_A, *QO = S + O_QO, *TQ = S + O_TQ, *U = S + O_U, *V = S + O_V, *X = S + O_X, *PW = S + O_PW;
-    double *ER = S + O_ER, *INV = S + O_INV, *SC = S + O_SC;
+    double *ER = S + O_ER, *INV = S + O_INV, *SC = S + O_SC, *SCA = S + O_SCA, *QS = SCA + q.N * ELL_SCW;
     const double t = q.Ts;
 
     for (int e = lane; e < ELL_KP; e += 32) INV[e] = 1.0 / (double)(e + 1);
@@ -125,10 +131,8 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
         for (int j = 0; j < ELL_KP; j++) { PW[j * ELL_Q + e] = pw; pw *= ELL_XI[e]; }
     }
     for (int e = lane; e < 81; e += 32) QO[e] = (e / 9 == e % 9) ? q.epsilon * q.epsilon : 0.0;   // Q_init = eps^2 I (:487)
-    double q2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    __syncwarp();
-
-    for (int i = 0; i < q.N; i++) {
+    // ---- updateMatrix + eulerToRot for every stage at once (lane = stage): they depend on the plan only ----
+    for (int i = lane; i < q.N; i += 32) {
         const double* zi = q.z + ((size_t)b * q.N + i) * 17;
         const double thrust = zi[3], v1 = zi[11], v2 = zi[12], v3 = zi[13], roll = zi[14], pitch = zi[15], yaw = zi[16];
         double sr, cr, sp, cp, sy, cy;
@@ -137,14 +141,46 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
         const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
                              sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
                              -sp, cp * sr, cp * cr};
-        // ---- E_i = sqrtm(Q), Q = Q1 (+) Q2 (:503-512); every lane redundantly, lane 0 stores ----
+        double* sc = SCA + i * ELL_SCW;
+        const double comb0 = thrust * 1.0 / q.mass, drag = q.drag;
+        const double comb5 = cp * sp, comb6 = cp * sr, comb7 = cp * cr, comb8 = sp * cr, comb9 = sp * sr;
+        const double comb1 = cr * sy - comb9 * cy, comb2 = sr * cy - comb8 * sy;
+        const double comb3 = cr * cy + comb9 * sy, comb4 = sr * sy + comb8 * cy;
+        const double cp2 = cp * cp, sp2 = sp * sp, cy2 = cy * cy, sy2 = sy * sy, sr2 = sr * sr;
+        const double t10 = comb6 * comb4 - comb7 * comb1, t11 = comb3 * comb4 + comb1 * comb2, t12 = comb6 * comb2 - comb7 * comb3;
+        const double t20 = cy * (sp2 - cp2 + cp2 * sr2) + comb9 * comb1;
+        const double t21 = 2 * comb5 * cy * sy - comb6 * (cy * comb3 + sy * comb1);
+        const double t22 = sy * (cp2 - sp2 - cp2 * sr2) + comb9 * comb3;
+        const double t30 = 2 * drag * (comb3 * comb1 - cp2 * cy * sy), t31 = drag * (comb6 * comb3 - comb5 * sy);
+        const double t32 = drag * (comb3 * comb3 - comb1 * comb1 - cp2 * cy2 + cp2 * sy2), t33 = drag * (comb6 * comb1 + comb5 * cy);
+        // a[r][c]: r = vel row (3..5), c = roll / pitch / yaw column (6..8)
+        sc[0] = comb0 * comb1 + drag * (v3 * t10 + v2 * t11 - 2 * v1 * comb4 * comb1);
+        sc[3] = -comb0 * comb3 + drag * (v1 * t11 - v3 * t12 - 2 * v2 * comb3 * comb2);
+        sc[6] = -comb0 * comb6 + drag * (v1 * t10 - v2 * t12 + 2 * v3 * comb7 * comb6);
+        sc[1] = comb0 * comb7 * cy + drag * (v3 * t20 - v2 * t21 - v1 * 2 * (comb5 * cy2 + comb6 * comb1 * cy));
+        sc[4] = comb0 * comb7 * sy - drag * (v3 * t22 - v1 * t21 - v2 * 2 * (comb5 * sy2 - comb6 * comb3 * sy));
+        sc[7] = -comb0 * comb8 + drag * (v1 * t20 - v2 * t22 + v3 * 2 * (comb5 - comb5 * sr2));
+        sc[2] = comb0 * comb2 + (v1 * t30 - v3 * t31 - v2 * t32);
+        sc[5] = comb0 * comb4 + (-v1 * t32 - v3 * t33 - v2 * t30);
+        sc[8] = -v2 * t33 - v1 * t31;
+        const double er = q.ego_r * q.ego_r, eh = q.ego_h * q.ego_h;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                sc[9 + 3 * r + c] = drag * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]);   // R diag(d,d,0) R'
+                sc[21 + 3 * r + c] = er * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]) + eh * R[3 * r + 2] * R[3 * c + 2];   // Q1 = R ego R' (:503)
+            }
+        sc[18] = comb4 / q.mass; sc[19] = -comb2 / q.mass; sc[20] = comb7 / q.mass;
+    }
+    double q2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    __syncwarp();
+
+    for (int i = 0; i < q.N; i++) {
+        // ---- Q_i = Q1 (+) Q2 (:503-510); its square root is taken for all stages at once after the loop ----
         {
-            const double er = q.ego_r * q.ego_r, eh = q.ego_h * q.ego_h;
-            double q1[9], qq[9], ee[9];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) q1[3 * r + c] = er * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]) + eh * R[3 * r + 2] * R[3 * c + 2];
+            const double* q1 = SCA + i * ELL_SCW + 21;
+            double qq[9];
             if (i == 0) {
 #pragma unroll
                 for (int e = 0; e < 9; e++) qq[e] = q1[e];
@@ -153,35 +189,14 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
 #pragma unroll
                 for (int e = 0; e < 9; e++) qq[e] = (1.0 + 1.0 / beta) * q1[e] + (1.0 + beta) * q2[e];
             }
-            sqrtm3_sym(qq, ee);
-            if (lane < 9) q.ellipsoid[((size_t)b * q.N + i) * 9 + lane] = ee[lane];
+            if (lane == 0) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) QS[i * 9 + e] = qq[e];
+            }
         }
-        // ---- updateMatrix: the stage's scalars -> SC: a[3][3] = At(3:6, 6:9), RDR'[3][3] = At(3:6, 3:6), bt[3] = Bt(3:6, 3) ----
-        if (lane == 0) {
-            const double comb0 = thrust * 1.0 / q.mass, drag = q.drag;
-            const double comb5 = cp * sp, comb6 = cp * sr, comb7 = cp * cr, comb8 = sp * cr, comb9 = sp * sr;
-            const double comb1 = cr * sy - comb9 * cy, comb2 = sr * cy - comb8 * sy;
-            const double comb3 = cr * cy + comb9 * sy, comb4 = sr * sy + comb8 * cy;
-            const double cp2 = cp * cp, sp2 = sp * sp, cy2 = cy * cy, sy2 = sy * sy, sr2 = sr * sr;
-            const double t10 = comb6 * comb4 - comb7 * comb1, t11 = comb3 * comb4 + comb1 * comb2, t12 = comb6 * comb2 - comb7 * comb3;
-            const double t20 = cy * (sp2 - cp2 + cp2 * sr2) + comb9 * comb1;
-            const double t21 = 2 * comb5 * cy * sy - comb6 * (cy * comb3 + sy * comb1);
-            const double t22 = sy * (cp2 - sp2 - cp2 * sr2) + comb9 * comb3;
-            const double t30 = 2 * drag * (comb3 * comb1 - cp2 * cy * sy), t31 = drag * (comb6 * comb3 - comb5 * sy);
-            const double t32 = drag * (comb3 * comb3 - comb1 * comb1 - cp2 * cy2 + cp2 * sy2), t33 = drag * (comb6 * comb1 + comb5 * cy);
-            // a[r][c]: r = vel row (3..5), c = roll / pitch / yaw column (6..8)
-            SC[0] = comb0 * comb1 + drag * (v3 * t10 + v2 * t11 - 2 * v1 * comb4 * comb1);
-            SC[3] = -comb0 * comb3 + drag * (v1 * t11 - v3 * t12 - 2 * v2 * comb3 * comb2);
-            SC[6] = -comb0 * comb6 + drag * (v1 * t10 - v2 * t12 + 2 * v3 * comb7 * comb6);
-            SC[1] = comb0 * comb7 * cy + drag * (v3 * t20 - v2 * t21 - v1 * 2 * (comb5 * cy2 + comb6 * comb1 * cy));
-            SC[4] = comb0 * comb7 * sy - drag * (v3 * t22 - v1 * t21 - v2 * 2 * (comb5 * sy2 - comb6 * comb3 * sy));
-            SC[7] = -comb0 * comb8 + drag * (v1 * t20 - v2 * t22 + v3 * 2 * (comb5 - comb5 * sr2));
-            SC[2] = comb0 * comb2 + (v1 * t30 - v3 * t31 - v2 * t32);
-            SC[5] = comb0 * comb4 + (-v1 * t32 - v3 * t33 - v2 * t30);
-            SC[8] = -v2 * t33 - v1 * t31;
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) SC[9 + 3 * r + c] = drag * (R[3 * r] * R[3 * c] + R[3 * r + 1] * R[3 * c + 1]);   // R diag(d,d,0) R'
-            SC[18] = comb4 / q.mass; SC[19] = -comb2 / q.mass; SC[20] = comb7 / q.mass;
+        {   // this stage's linearisation scalars
+            const double* sc = SCA + i * ELL_SCW;
+            if (lane < 21) SC[lane] = sc[lane];
         }
         __syncwarp();
         // ---- A = Phi t = (At + Bt Kt) t ----
@@ -285,6 +300,16 @@ __global__ void __launch_bounds__(32 * ELL_WARPS) ellipsoid_propagate_kernel(con
                 q2[3 * r + c] = acc;
             }
         __syncwarp();
+    }
+    // ---- E_i = sqrtm(Q_i) (:511-512), one stage per lane ----
+    for (int i = lane; i < q.N; i += 32) {
+        double qq[9], ee[9];
+#pragma unroll
+        for (int e = 0; e < 9; e++) qq[e] = QS[i * 9 + e];
+        sqrtm3_sym(qq, ee);
+        double* out = q.ellipsoid + ((size_t)b * q.N + i) * 9;
+#pragma unroll
+        for (int e = 0; e < 9; e++) out[e] = ee[e];
     }
 }
 
