@@ -11,6 +11,6 @@ for n in 1 2 4 8; do
   fi
   tail -c 300 gpurun_out/scale_$n.json
 done
-timeout 900 python scripts/run_configs.py --config 3 > gpurun_out/config3_full.json 2> gpurun_out/config3.err; tail -c 400 gpurun_out/config3_full.json
+timeout 900 python tests/tools/run_configs.py --config 3 > gpurun_out/config3_full.json 2> gpurun_out/config3.err; tail -c 400 gpurun_out/config3_full.json
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 \
-  scripts/run_configs.py --config 4 > gpurun_out/config4_full_8gpu.json 2> gpurun_out/config4.err; tail -c 400 gpurun_out/config4_full_8gpu.json
+  tests/tools/run_configs.py --config 4 > gpurun_out/config4_full_8gpu.json 2> gpurun_out/config4.err; tail -c 400 gpurun_out/config4_full_8gpu.json

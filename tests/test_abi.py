@@ -86,10 +86,12 @@ def test_no_cpu_fallback_without_a_device(cuda_lib):
 
 
 def test_product_never_touches_the_oracle():
-    pkg = os.path.join(ROOT, "forces_resilient_planner_b200")
-    for dirpath, _, files in os.walk(pkg):
+    """Neither the package nor the measurement scripts may import, link or execute anything under oracle/
+    (only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may)."""
+    for top in ("forces_resilient_planner_b200", "scripts"):
+      for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
         for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h", ".sh")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "libnmpc_oracle" not in txt and not re.search(r'#include\s*[<"][^>"]*oracle', txt), fn

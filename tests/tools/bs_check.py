@@ -1,4 +1,4 @@
-"""kkt_backsolve_kernel: correctness against the Schur oracle (fp64 / fp32, N = 20 / 40) and CUDA-event
+"""Test tool (uses the CPU oracle as the checker, hence under tests/).  kkt_backsolve_kernel: correctness against the Schur oracle (fp64 / fp32, N = 20 / 40) and CUDA-event
 timings at the bench size.  GPU only."""
 import json
 import os
@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from forces_resilient_planner_b200 import kkt  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 

@@ -1,7 +1,8 @@
-"""Full-size runs of BASELINE configs 3 and 4 (parity-test configs, not the bench line).
+"""Test tool (config 3 is checked against the CPU oracle on a sample, hence under tests/).
+Full-size runs of BASELINE configs 3 and 4 (parity-test configs, not the bench line).
 
-  python scripts/run_configs.py --config 3                       # 1 GPU: B = 65536, N = 20, 4-10 rows
-  torchrun --nproc-per-node 8 ... scripts/run_configs.py --config 4   # 8 GPUs: B = 262144, N = 40, wind sweep,
+  python tests/tools/run_configs.py --config 3                       # 1 GPU: B = 65536, N = 20, 4-10 rows
+  torchrun --nproc-per-node 8 ... tests/tools/run_configs.py --config 4   # 8 GPUs: B = 262144, N = 40, wind sweep,
                                                                        # NCCL all-gather of the results
 
 Each prints one JSON line: solves/s (CUDA events around the fused launch), converged fraction,
@@ -10,7 +11,7 @@ plus (config 3) parity against the CPU oracle on a 2048-problem sample and (conf
 the end-of-batch all-gather with a checksum-of-checksums check.
 """
 import argparse, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
