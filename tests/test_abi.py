@@ -88,10 +88,44 @@ def test_no_cpu_fallback_without_a_device(cuda_lib):
 def test_product_never_touches_the_oracle():
     """Neither the package nor the measurement scripts may import, link or execute anything under oracle/
     (only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may)."""
+    sources = []
     for top in ("forces_resilient_planner_b200", "scripts"):
-      for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h", ".sh")):
-                txt = open(os.path.join(dirpath, fn)).read()
-                assert "import oracle" not in txt and "from oracle" not in txt, fn
-                assert "libnmpc_oracle" not in txt and not re.search(r'#include\s*[<"][^>"]*oracle', txt), fn
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            sources += [os.path.join(dirpath, fn) for fn in files
+                        if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h", ".sh"))]
+    assert len(sources) > 20
+    for path in sources:
+        txt = open(path).read()
+        assert "import oracle" not in txt and "from oracle" not in txt, path
+        assert "libnmpc_oracle" not in txt and not re.search(r'#include\s*[<"][^>"]*oracle', txt), path
+
+
+def test_argument_checks_of_the_kernels_around_the_solve(cuda_lib):
+    """Bad sizes / null pointers are rejected with a negative NMPC_ERR_ARG code before any CUDA call,
+    so this runs without a GPU."""
+    vp = ctypes.c_void_p
+    one = ctypes.c_void_p(16)          # any non-null pointer: never dereferenced on these paths
+    f = cuda_lib.nmpc_sample_reference_f64
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 9
+    assert f(4, 20, 8, 0.0, one, one, one, one, None, one, one, None, None) < 0          # Ts must be positive
+    assert f(4, 20, 8, 0.05, None, one, one, one, None, one, one, None, None) < 0        # null path
+    assert f(0, 20, 8, 0.05, None, None, None, None, None, None, None, None, None) == 0  # empty batch is a no-op
+    g = cuda_lib.nmpc_propagate_ellipsoids_f64
+    g.restype = ctypes.c_int
+    g.argtypes = [ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(_lib.EllipsoidConsts), vp, vp]
+    c = _lib.EllipsoidConsts()
+    cuda_lib.nmpc_default_ellipsoid_consts(ctypes.byref(c))
+    assert (c.mass, c.drag, c.ego_r, c.ego_h, c.ext_noise_bound, c.epsilon, c.Ts) == (0.745319, 0.33, 0.27, 0.0425, 0.5, 0.06, 0.05)
+    assert g(4, 20, None, ctypes.byref(c), one, None) < 0
+    c.mass = 0.0
+    assert g(4, 20, one, ctypes.byref(c), one, None) < 0                                 # bad constants
+    h = cuda_lib.nmpc_select_corridors_f64
+    h.restype = ctypes.c_int
+    h.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_longlong] + [vp] * 4 + [ctypes.POINTER(ctypes.c_double)] + [vp] * 7
+    args = [one, 3 * 64, one, one, one, one, None, one, one, one, one, one, one, None]
+    assert h(4, 20, 64, 8, 6, *args) < 0                                                 # fewer than 7 rows cannot hold the box
+    assert h(4, 20, 64, 0, 30, *args) < 0
+    bad = list(args); bad[1] = 10                                                        # stride shorter than a cloud
+    assert h(4, 20, 64, 8, 30, *bad) < 0
+    assert b"bad argument" in cuda_lib.nmpc_last_error()
