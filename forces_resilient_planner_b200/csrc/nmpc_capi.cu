@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstddef>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -86,6 +87,9 @@ int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* h
     if (B == 0) return 0;
     if (!xinit || !z0 || !hdr || !nrows || !z_out || !info_int || !info_real || (mcap > 0 && !rows))
         return fail(NMPC_ERR_ARG, "null pointer argument");
+    // the per-problem blocks are moved by TMA bulk copies / 16-byte vector loads
+    for (const void* p : {(const void*)z0, (const void*)hdr, (const void*)rows, (const void*)nrows, (const void*)z_out})
+        if (reinterpret_cast<uintptr_t>(p) & 15) return fail(NMPC_ERR_ARG, "device pointers must be 16-byte aligned");
     nmpc::Params<T> prm;
     prm.B = B; prm.mcap = mcap; prm.variant = variant;
     prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order;
@@ -142,6 +146,8 @@ int backsolve_device(int B, int N, const T* fac, const T* g, const T* d, T* dz, 
     if (B < 0 || !nmpc_supported_horizon(N)) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
     if (B == 0) return 0;
     if (!fac || !g || !d || !dz || !y) return fail(NMPC_ERR_ARG, "null pointer argument");
+    for (const void* p : {(const void*)fac, (const void*)g, (const void*)d, (const void*)dz, (const void*)y})
+        if (reinterpret_cast<uintptr_t>(p) & 15) return fail(NMPC_ERR_ARG, "device pointers must be 16-byte aligned");
     nmpc::BacksolveParams<T> q{B, fac, g, d, dz, y};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return N == 20 ? launch_backsolve<T, 20>(q, st) : launch_backsolve<T, 40>(q, st);

@@ -71,7 +71,9 @@ int nmpc_supported_horizon(int N);
 /* dynamic shared memory one problem occupies (bytes); elem_size 8 (f64) or 4 (f32) */
 long nmpc_smem_bytes(int N, int mcap, int elem_size);
 
-/* ---- device-pointer API: everything already resident in HBM, asynchronous on `stream` -------- */
+/* ---- device-pointer API: everything already resident in HBM, asynchronous on `stream` --------
+ * z0, hdr, rows, nrows and z_out must be 16-byte aligned (TMA bulk copies / 16-byte vector loads);
+ * a misaligned pointer is rejected with NMPC_ERR_ARG.                                           */
 int nmpc_solve_batch_f64(int B, int N, int mcap, const double *xinit, const double *z0,
                          const double *hdr, const double *rows, const int *nrows, int variant,
                          const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,

@@ -129,3 +129,12 @@ def test_argument_checks_of_the_kernels_around_the_solve(cuda_lib):
     bad = list(args); bad[1] = 10                                                        # stride shorter than a cloud
     assert h(4, 20, 64, 8, 30, *bad) < 0
     assert b"bad argument" in cuda_lib.nmpc_last_error()
+    # misaligned device pointers are rejected by the entry points that move per-problem blocks with TMA
+    k = cuda_lib.nmpc_kkt_backsolve_f64
+    k.restype = ctypes.c_int
+    k.argtypes = [ctypes.c_int, ctypes.c_int] + [vp] * 6
+    assert k(2, 20, vp(16), vp(32), vp(48), vp(64), vp(72), None) < 0 and b"16-byte" in cuda_lib.nmpc_last_error()
+    o = _lib.default_opts()
+    sv = cuda_lib.nmpc_solve_batch_f64
+    assert sv(2, 20, 6, vp(8), vp(16), vp(32), vp(40), vp(64), 0, ctypes.byref(o), vp(96), vp(128), vp(160), None) < 0
+    assert b"16-byte" in cuda_lib.nmpc_last_error()
