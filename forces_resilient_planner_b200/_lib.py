@@ -33,7 +33,7 @@ EXPORTS = [
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",
     "nmpc_backsolve_algorithmic_bytes",
-    "nmpc_pack_params_f64", "nmpc_shift_warm_start_f64", "nmpc_sample_reference_f64", "nmpc_default_ellipsoid_consts", "nmpc_propagate_ellipsoids_f64", "nmpc_select_corridors_f64",
+    "nmpc_pack_params_f64", "nmpc_shift_warm_start_f64", "nmpc_wrap_yaw_f64", "nmpc_sample_reference_f64", "nmpc_default_ellipsoid_consts", "nmpc_propagate_ellipsoids_f64", "nmpc_select_corridors_f64",
     "nmpc_fma_peak_probe",
     "FORCESNLPsolver_normal_solve", "FORCESNLPsolver_final_solve",
 ]

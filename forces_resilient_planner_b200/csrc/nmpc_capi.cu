@@ -518,6 +518,17 @@ int nmpc_propagate_ellipsoids_f64(int B, int N, const double* z, const nmpc_elli
     return 0;
 }
 
+int nmpc_wrap_yaw_f64(int B, int N, double* z, void* stream)
+{
+    if (B < 0 || N <= 0) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
+    if (B == 0) return 0;
+    if (!z) return fail(NMPC_ERR_ARG, "null pointer argument");
+    const int n = B * N;
+    nmpc::wrap_yaw_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n, z);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int nmpc_sample_reference_f64(int B, int N, int P, double Ts, const double* kino_path, const int* kino_size,
                               const double* t_off, const double* last_yaw, const double* pos1, double* ref_pos,
                               double* ref_yaw, int* hard_to_follow, void* stream)

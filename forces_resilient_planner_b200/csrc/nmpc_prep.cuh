@@ -99,6 +99,15 @@ __global__ void shift_warm_start_kernel(int B, int N, const double* z_prev, doub
         for (int j = 0; j < 9; j++) xinit[(size_t)b * 9 + j] = zd[8 + j];
 }
 
+// updateFORCESResults' yaw wrap (nmpc_solver.cpp:531-541) on an adopted plan, in place
+__global__ void wrap_yaw_kernel(int n_stages_total, double* z)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_stages_total) return;
+    const double v = z[(size_t)t * 17 + 16];
+    z[(size_t)t * 17 + 16] = v < -REF_PI ? v + 2 * REF_PI : (v > REF_PI ? v - 2 * REF_PI : v);
+}
+
 struct SampleParams {
     int B, N, P;
     double Ts;

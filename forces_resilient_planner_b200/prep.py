@@ -132,3 +132,17 @@ def select_corridors(cloud, cloud_n, ref_pos, ref_yaw, ellipsoid, max_polys=8, m
                   ref_yaw.data_ptr(), ellipsoid.data_ptr(), bb, poly_A.data_ptr(), poly_b.data_ptr(), poly_m.data_ptr(),
                   poly_idx.data_ptr(), n_poly.data_ptr(), overflow.data_ptr(), st.cuda_stream))
     return poly_A, poly_b, poly_m, poly_idx, n_poly, overflow
+
+
+def wrap_yaw(z, stream=None):
+    """updateFORCESResults' yaw wrap (nmpc_solver.cpp:531-541) on an adopted plan z [B,N,17] (cuda, float64), in place."""
+    import torch
+    lib = _lib.load()
+    B, N, _ = z.shape
+    fn = lib.nmpc_wrap_yaw_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    st = stream if stream is not None else torch.cuda.current_stream(z.device)
+    with torch.cuda.device(z.device):
+        _check(fn(B, N, z.data_ptr(), st.cuda_stream))
+    return z

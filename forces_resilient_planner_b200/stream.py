@@ -170,7 +170,7 @@ class PlannerPipeline:
     """One replan of the reference's `setFORCESParams` + `solveNormal` for B agents, device-resident end to end
     (SURVEY.md §8f rank 1-4 + the solve):
 
-        shift warm start        nmpc_shift_warm_start_f64      nmpc_solver.cpp:531-543, forces_normal.cpp:62-97
+        yaw wrap + shift        nmpc_wrap_yaw_f64, nmpc_shift_warm_start_f64   nmpc_solver.cpp:531-543, forces_normal.cpp:62-97
         disturbance ellipsoids  nmpc_propagate_ellipsoids_f64  :484-521, 567-699      (along the previous plan)
         references + yaw        nmpc_sample_reference_f64      :109-142, 834-862      (front-end polyline at Ts)
         corridors               nmpc_select_corridors_f64      :288-332, DecompROS    (obstacle cloud -> polytopes)
@@ -209,7 +209,7 @@ class PlannerPipeline:
         toff = torch.from_numpy(np.ascontiguousarray(t_off)).to(self.dev)
         prev = self.z                                                  # mpc_output_ of the last cycle (cold guess at first)
         if warm:
-            prep.shift_warm_start(prev, self.xinit, self.z0, wrap_yaw=True, stream=st)
+            prep.shift_warm_start(prev, self.xinit, self.z0, wrap_yaw=False, stream=st)   # prev is already wrapped (below)
         E = prep.propagate_ellipsoids(prev, stream=st)
         last_yaw = prev[:, 1, 16].contiguous(); pos1 = prev[:, 1, 8:11].contiguous()
         ref_pos, ref_yaw, far = prep.sample_reference(self.kino_path, self.kino_size, toff, last_yaw, self.N, self.Ts,
@@ -223,8 +223,10 @@ class PlannerPipeline:
                                              hdr.data_ptr(), rows.data_ptr(), nrows.data_ptr(), 0, ctypes.byref(o),
                                              z_new.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr(),
                                              ctypes.c_void_p(st.cuda_stream)))
+        cmd = z_new[:, 0, 0:4].cpu().numpy()
+        prep.wrap_yaw(z_new, stream=st)                  # updateFORCESResults (:531-541): the adopted plan is kept wrapped
         self.z = z_new
         self.cycle += 1
         self.last = dict(ellipsoid=E, ref_pos=ref_pos, ref_yaw=ref_yaw, hard_to_follow=far, poly_idx=pidx, n_poly=npoly,
                          overflow=ovf, hdr=hdr, rows=rows, nrows=nrows)
-        return self.z[:, 0, 0:4].cpu().numpy(), self.info_int[:, 0].cpu().numpy(), self.info_int[:, 1].cpu().numpy()
+        return cmd, self.info_int[:, 0].cpu().numpy(), self.info_int[:, 1].cpu().numpy()

@@ -144,6 +144,9 @@ int nmpc_pack_params_f64(int B, int N, int P, int M, int mcap, const double *ref
                          int *nrows, void *cuda_stream);
 int nmpc_shift_warm_start_f64(int B, int N, const double *z_prev, double *xinit, double *z0,
                               int wrap_yaw, void *cuda_stream);
+/* NMPCSolver::updateFORCESResults' yaw wrap (nmpc_solver.cpp:531-541) on an adopted plan z [B][N][17], in place:
+ * yaw < -PI -> yaw + 2 PI, yaw > PI -> yaw - 2 PI, with the reference's PI = 3.1415926 (:3).               */
+int nmpc_wrap_yaw_f64(int B, int N, double *z, void *cuda_stream);
 
 /* ---- reference sampling + yaw reference, device-resident ---------------
  * Batched NMPCSolver::getCurTraj (plan_manage/src/nmpc_solver.cpp:109-142) + calculate_yaw

@@ -114,6 +114,8 @@ def test_shift_warm_start_matches_reference_shift():
     xinit, z0 = prep.shift_warm_start(_t(z), wrap_yaw=True)
     x_ref, z_ref = W.shift_warm_start(PN.wrap_yaw(z))          # the reference's wrap, with its own PI = 3.1415926
     assert np.allclose(z0.cpu().numpy(), z_ref, atol=0, rtol=0) and np.array_equal(xinit.cpu().numpy(), x_ref)
+    zd = _t(z)
+    assert prep.wrap_yaw(zd) is zd and np.array_equal(zd.cpu().numpy(), PN.wrap_yaw(z))       # updateFORCESResults, in place
 
 
 def test_sample_reference_matches_getCurTraj_and_calculate_yaw():

@@ -203,6 +203,11 @@ def test_cpp_dropin_demo_runs_the_planner_call_sequence():
     out = subprocess.run([os.path.join(host, "dropin_demo")], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("exitflag 1") == 4
+    # host/pipeline_demo.cpp: three closed-loop fleet replans (shift, ellipsoids, references, corridors, pack, solve)
+    # through the device-pointer C ABI only, from C++
+    out = subprocess.run([os.path.join(host, "pipeline_demo")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("64/64 accepted") == 3 and out.stdout.count("corridor overflow 0") == 3, out.stdout
 
 
 def test_fp32_entry_point_at_its_stated_tolerance():
@@ -312,8 +317,7 @@ def test_planner_pipeline_matches_cpu_twin():
         cmd, flag, it = pipe.replan(ext, t_off)
         # ---- CPU twin ----
         if cyc > 0:
-            prev_w = PN.wrap_yaw(prev)
-            x_c, z0_c = W.shift_warm_start(prev_w)
+            x_c, z0_c = W.shift_warm_start(prev)
         E = EN.propagate_batch(prev)
         rp, ry, far = PN.sample_reference(paths, size, t_off, prev[:, 1, 16], N, Ts, pos1=prev[:, 1, 8:11])
         pA = np.zeros((B, 20, mcap, 3)); pb = np.zeros((B, 20, mcap)); pm = np.zeros((B, 20), np.int32); pidx = np.zeros((B, N), np.int32)
@@ -332,7 +336,7 @@ def test_planner_pipeline_matches_cpu_twin():
         assert np.all(flag == 1) and np.all(c["flag"] == 1), (cyc, flag, c["flag"])
         assert np.array_equal(it, c["it"]), cyc
         assert np.max(np.abs(cmd - c["z"][:, 0, 0:4])) < 1e-6, cyc
-        prev = c["z"]
+        prev = PN.wrap_yaw(c["z"])                       # updateFORCESResults: the adopted plan is kept wrapped
     # the vehicles actually follow their paths
     assert np.max(np.linalg.norm(prev[:, 1, 8:11] - rp[:, 0], axis=1)) < 0.3
 
