@@ -20,3 +20,4 @@ torch.cuda.synchronize(); print("sample + ellipsoids ok", float(E.abs().max()))
 cloud = t(rng.uniform([-1, -2, 0], [5, 2, 2], (200, 3))); ref = np.zeros((3, 20, 3)); ref[:, :, 0] = 0.2 * np.arange(20); ref[:, :, 2] = 1.0
 out = prep.select_corridors(cloud, torch.tensor([200], dtype=torch.int32).cuda(), t(ref), t(np.zeros((3, 20))), E, max_polys=20, max_rows=30)
 torch.cuda.synchronize(); print("corridors ok", out[4].tolist(), out[5].tolist())
+zz = t(np.random.default_rng(2).normal(scale=3.0, size=(4, 20, 17))); prep.wrap_yaw(zz); torch.cuda.synchronize(); print("wrap ok")
