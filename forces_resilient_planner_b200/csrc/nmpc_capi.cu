@@ -60,19 +60,24 @@ int fail(int code, const char* fmt, ...)
             return fail(NMPC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));     \
     } while (0)
 
-template <typename T, int N>
-int launch(const nmpc::Params<T>& prm, cudaStream_t st)
+template <typename T, int N, bool PC>
+int launch_pc(const nmpc::Params<T>& prm, cudaStream_t st)
 {
-    using L = nmpc::Layout<T, N>;
+    using L = nmpc::Layout<T, N, PC>;
     const size_t smem = L::bytes(prm.mcap);
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::nmpc_ipm_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(nmpc::nmpc_ipm_kernel<T, N, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    nmpc::nmpc_ipm_kernel<T, N><<<prm.B, 32, smem, st>>>(prm);
+    nmpc::nmpc_ipm_kernel<T, N, PC><<<prm.B, 32, smem, st>>>(prm);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+template <typename T, int N>
+int launch(const nmpc::Params<T>& prm, cudaStream_t st)
+{
+    return prm.o.pc ? launch_pc<T, N, true>(prm, st) : launch_pc<T, N, false>(prm, st);
 }
 
 template <typename T>
@@ -363,6 +368,7 @@ void nmpc_default_opts(nmpc_opts* o)
     o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-4;
     o->kappa_push = 1e-2; o->s_floor = 1e-2;
     o->maxit = 200; o->max_bt = 6;
+    o->pc = 0; o->reserved = 0;
 }
 
 void nmpc_default_opts_f32(nmpc_opts* o)

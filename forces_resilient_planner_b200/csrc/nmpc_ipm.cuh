@@ -31,7 +31,7 @@ namespace nmpc {
 
 struct Opts {
     double mu0, sigma, mu_floor, tol_stat, tol_eq, tol_ineq, tol_comp, kappa_push, s_floor;
-    int maxit, max_bt;
+    int maxit, max_bt, pc, reserved;
 };
 
 template <typename T> struct Params {
@@ -66,7 +66,7 @@ template <typename T> struct Params {
 // registers (the sweeps use few registers, the evaluation phases that need many do not run then),
 // and restores it afterwards.  That is 15.6 KB less shared memory per problem (fp64, N = 20) and
 // one more resident warp per SM -- occupancy is what bounds this kernel.
-template <typename T, int N> struct Layout {
+template <typename T, int N, bool PC = false> struct Layout {
     static_assert(N % 4 == 0 && N >= 4 && N <= 64, "horizon must be a multiple of 4 (TMA 16-byte granules)");
     static constexpr int HDR_S = 11;    // padded stage-header stride (bank-conflict free)
     static constexpr int PHI_S = 21;    // 17 diagonal + 3 off-diagonal of the position block + u/u_prev coupling
@@ -87,7 +87,7 @@ template <typename T, int N> struct Layout {
     // ---- O (overlay at offset 0): Riccati / rollout scratch first, gains last ----
     static constexpr int PN = 0;                 // 13x13 cost-to-go
     static constexpr int PF = PN + 169;          // 13x13 = PN(:, x) * F    (F = d x+ / d(u, x), 9x13, never formed)
-    static constexpr int GG = PF + 169;          // 13x13 = F' * PF(x, :)
+    static constexpr int GG = PC ? PF : PF + 169;   // 13x13 = F' * PF(x, :); with PC it overwrites PF (after a warp barrier)
     static constexpr int TV = GG + 169;          // 13    = p+ + PN d
     static constexpr int QUU = TV + 13;          // 4x4
     static constexpr int QUR = QUU + 16;         // 4x13  [Q_ux | Q_uq]
@@ -97,7 +97,9 @@ template <typename T, int N> struct Layout {
     static constexpr int Y0 = YS + 52;           // 4     L^-1 QV
     static constexpr int DXI = Y0 + 4;           // 13
     static constexpr int KFF = DXI + 14;
-    static constexpr int KG = KFF + N * 4;
+    static constexpr int QINV = KFF + N * 4;                 // PC: Quu^-1 packed lower per stage (the corrector re-uses the factorisation)
+    static constexpr int PQQ0 = QINV + (PC ? N * 10 : 0);    // PC: the q-block of P_0 (stage-0 solve of the corrector)
+    static constexpr int KG = PQQ0 + (PC ? 10 : 0);
     static constexpr int O_END = KG + N * 52;
     // words parked in registers across the sweeps: at most 64 per lane; if the overlay is larger
     // (long horizons) the gains are placed in SH instead of being overlaid
@@ -117,7 +119,9 @@ template <typename T, int N> struct Layout {
     static constexpr int SH_JC = SH_D + N * NXI;
     static constexpr int SH_PHID = SH_JC + N * NJC;         // last stage's Jacobian slot unused by the solver
     static constexpr int SH_KG = SH_PHID + N * PHI_S;       // only when the gains are not overlaid
-    static constexpr int SH_END = SH_KG + (KG_OVERLAID ? 0 : N * 52);
+    static constexpr int SH_DZAP = SH_KG + (KG_OVERLAID ? 0 : N * 52);   // PC: position part of the affine step, [N][3]
+    static constexpr int SH_END = SH_DZAP + (PC ? N * 3 : 0);
+    static constexpr int NT = (N * NZ + 31) / 32;           // flat (stage, variable) pairs per lane
     __host__ __device__ static constexpr int total_T(int mcap) { return sh_off(mcap) + SH_END; }
     __host__ __device__ static constexpr size_t bytes(int mcap)
     {
@@ -245,8 +249,8 @@ template <typename T, int n, int sa, int sb> __device__ __forceinline__ T dot3(c
 // =====================================================================================
 // per-warp solver state: thin view over the shared-memory block
 // =====================================================================================
-template <typename T, int N> struct Solver {
-    using L = Layout<T, N>;
+template <typename T, int N, bool PC = false> struct Solver {
+    using L = Layout<T, N, PC>;
     using C = Const<T>;
     T* sm;        // T region
     int* nr;      // live rows per stage
@@ -254,6 +258,7 @@ template <typename T, int N> struct Solver {
     const T* rows_g;   // this problem's corridor rows in global memory, [N][mcap][4] = (a0 a1 a2 b)
     bool final_variant;
     T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *S, *LC, *BND;
+    T *QINV, *PQQ0, *DZAP;   // predictor-corrector only
     T* fac_out = nullptr;   // when set, riccati_backward streams the factor ([P: N x 91][K | Quu^-1 | J: N x 113]) to HBM
 
     __device__ __forceinline__ void bind(unsigned char* smem_raw, int lane_, int mcap_)
@@ -268,6 +273,7 @@ template <typename T, int N> struct Solver {
         DZ = sh + L::SH_DZ; G = sh + L::SH_G; P = sh + L::SH_P; D = sh + L::SH_D; JC = sh + L::SH_JC; PHID = sh + L::SH_PHID;
         KG = L::KG_OVERLAID ? sm + L::KG : sh + L::SH_KG;
         KFF = sm + L::KFF;
+        QINV = sm + L::QINV; PQQ0 = sm + L::PQQ0; DZAP = sh + L::SH_DZAP;
     }
     // registers <-> the slice of R that the sweep-private overlay is about to overwrite
     __device__ __forceinline__ void park(T (&regs)[L::NPARK_LANE]) const
@@ -279,6 +285,14 @@ template <typename T, int N> struct Solver {
     {
 #pragma unroll
         for (int t = 0; t < L::NPARK_LANE; t++) sm[lane + 32 * t] = regs[t];
+    }
+
+    // exchange the parked registers with shared memory in place: after the first call the stage-phase state R is back
+    // in shared memory and the sweep-private arrays (gains, Quu^-1, ...) wait in the registers; the second call undoes it
+    __device__ __forceinline__ void swap_parked(T (&regs)[L::NPARK_LANE]) const
+    {
+#pragma unroll
+        for (int t = 0; t < L::NPARK_LANE; t++) { const T tmp = sm[lane + 32 * t]; sm[lane + 32 * t] = regs[t]; regs[t] = tmp; }
     }
 
     __device__ __forceinline__ int live(int k) const { return k == 0 ? 0 : min(nr[k], mcap); }
@@ -504,12 +518,12 @@ template <typename T, int N> struct Solver {
                 }
                 __syncwarp();
                 // ---- phase B: lane = column of PF (v-ordering); lane 13 = the vector tv ----------
+                T g[13];
                 if (lane < 14) {
                     const T* col = lane < 13 ? PF + lane : TV;
                     const int cs = lane < 13 ? 13 : 1;
                     const T xp[3] = {col[0], col[cs], col[2 * cs]}, xv[3] = {col[3 * cs], col[4 * cs], col[5 * cs]};
                     const T xa[3] = {col[6 * cs], col[7 * cs], col[8 * cs]};
-                    T g[13];
                     ft_times(jc, xp, xv, xa, g);
                     if (lane < 4) {                                // column of Q_uu and of Q_xu = Q_ux'
                         const int j = lane;
@@ -521,10 +535,7 @@ template <typename T, int N> struct Solver {
                         }
 #pragma unroll
                         for (int i = 4; i < 13; i++) QUR[j * 13 + i - 4] = g[i] + PF[(9 + j) * 13 + i];
-                    } else if (lane < 13) {                        // column of Q_xx (phase D reads the lower triangle)
-#pragma unroll
-                        for (int i = 4; i < 13; i++) GG[i * 13 + lane] = g[i];
-                    } else {                                       // q~ = g + F' tv (+ the q+ = u part of tv)
+                    } else if (lane == 13) {                       // q~ = g + F' tv (+ the q+ = u part of tv)
 #pragma unroll
                         for (int w = 0; w < 4; w++) QV[w] = g[w] + (gk[w] + TV[9 + w]);
 #pragma unroll
@@ -532,6 +543,11 @@ template <typename T, int N> struct Solver {
                     }
                 } else if (lane >= 16 && lane < 20) {
                     QXI[9 + lane - 16] = gk[4 + lane - 16];
+                }
+                if (PC) __syncwarp();                              // GG overwrites PF: every read of PF is behind us
+                if (lane >= 4 && lane < 13) {                      // column of Q_xx (phase D reads the lower triangle)
+#pragma unroll
+                    for (int i = 4; i < 13; i++) GG[i * 13 + lane] = g[i];
                 }
                 if (lane < 16) QUR[(lane >> 2) * 13 + 9 + (lane & 3)] = ((lane >> 2) == (lane & 3)) ? phi[20] : T(0);
             } else {
@@ -553,19 +569,29 @@ template <typename T, int N> struct Solver {
                 a[12] = QUU[12]; a[13] = QUU[13]; a[14] = QUU[14]; a[15] = QUU[15];
                 ok &= chol4<T>(a, l, li);
             }
-            if (lane < 14) {
+            if (lane < (PC ? 18 : 14)) {
                 T x[4];
 #pragma unroll
-                for (int r = 0; r < 4; r++) x[r] = (lane < 13) ? QUR[r * 13 + lane] : QV[r];
+                for (int r = 0; r < 4; r++) x[r] = (lane < 13) ? QUR[r * 13 + lane] : (lane == 13 ? QV[r] : (r == lane - 14 ? T(1) : T(0)));
                 fsub4<T>(l, li, x);
-                T* ys = (lane < 13) ? YS + lane : Y0;
-                const int ystr = (lane < 13) ? 13 : 1;
+                if (lane < 14) {
+                    T* ys = (lane < 13) ? YS + lane : Y0;
+                    const int ystr = (lane < 13) ? 13 : 1;
 #pragma unroll
-                for (int r = 0; r < 4; r++) ys[r * ystr] = x[r];
+                    for (int r = 0; r < 4; r++) ys[r * ystr] = x[r];
+                }
                 bsub4<T>(l, li, x);
-                T* kg = (lane < 13) ? KG + k * 52 + lane : KFF + k * 4;
+                if (lane < 14) {
+                    T* kg = (lane < 13) ? KG + k * 52 + lane : KFF + k * 4;
+                    const int ystr = (lane < 13) ? 13 : 1;
 #pragma unroll
-                for (int r = 0; r < 4; r++) kg[r * ystr] = -x[r];
+                    for (int r = 0; r < 4; r++) kg[r * ystr] = -x[r];
+                } else {                                           // PC: column lane - 14 of Quu^-1, packed lower
+                    const int c = lane - 14;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (r >= c) QINV[k * 10 + r * (r + 1) / 2 + c] = x[r];
+                }
             }
             __syncwarp();
             // ---- phase D ------------------------------------------------------------------------
@@ -611,17 +637,25 @@ template <typename T, int N> struct Solver {
     // ------------------------------------------------------------- forward rollout ------
     // dz_k = (du, dq, dx): du = K dxi + kff (8 lanes per row + shuffles); dxi+ = [F (du, dx) + d_x ; du + d_q]
     // with the rows of F addressed through per-lane offsets into the compact Jacobian (branch-free).
-    __device__ bool rollout()
+    // DELTA (predictor-corrector): the same rollout for the correction of the step -- zero defects, feed-forward terms
+    // and p_0 from delta_backward(), the q-block of P_0 saved by the first rollout, dz accumulated
+    template <bool DELTA = false> __device__ bool rollout()
     {
-        T* PN = sm + L::PN; T* DXI = sm + L::DXI;
+        T* PN = sm + L::PN; T* DXI = sm + L::DXI; T* TV = sm + L::TV;
         bool ok = true;
         {   // stage 0: x fixed (dx = 0), u_prev free: dq = -Pqq^-1 p_q
             T a[16], l[10], li[4], x[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) {
 #pragma unroll
-                for (int c = 0; c <= r; c++) a[4 * r + c] = PN[(9 + r) * 13 + 9 + c];
-                x[r] = -P[9 + r];
+                for (int c = 0; c <= r; c++) a[4 * r + c] = DELTA ? PQQ0[r * (r + 1) / 2 + c] : PN[(9 + r) * 13 + 9 + c];
+                x[r] = DELTA ? -TV[9 + r] : -P[9 + r];
+            }
+            if (PC && !DELTA && lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c <= r; c++) PQQ0[r * (r + 1) / 2 + c] = a[4 * r + c];
             }
             ok = chol4<T>(a, l, li);
             fsub4<T>(l, li, x);
@@ -655,7 +689,10 @@ template <typename T, int N> struct Solver {
             const T du_l = __shfl_sync(0xffffffffu, acc, 8 * (lane & 3));   // du[lane & 3]
             const T du_s = __shfl_sync(0xffffffffu, acc, duSrc);            // du feeding row `lane` of dxi+
             const T self = DXI[lrow];
-            if (lane < NZ) DZ[k * NZ + lane] = (lane < 4) ? du_l : (lane < 8 ? DXI[5 + lane] : DXI[lane - 8]);
+            if (lane < NZ) {
+                const T v = (lane < 4) ? du_l : (lane < 8 ? DXI[5 + lane] : DXI[lane - 8]);
+                if (DELTA) DZ[k * NZ + lane] += v; else DZ[k * NZ + lane] = v;
+            }
             T nxt = T(0);
             if (k < N - 1) {
                 const T* jc = JC + k * NJC;
@@ -663,13 +700,150 @@ template <typename T, int N> struct Solver {
                 const T m1 = jc[offV + 1] * DXI[4] + jc[offR + 1] * DXI[7];
                 const T m2 = jc[offV + 2] * DXI[5] + jc[offR + 2] * DXI[8];
                 const T mw = jc[offW] * dw0 + jc[offW + 1] * dw1 + jc[offW + 2] * dw2;
-                nxt = D[k * NXI + lrow] + mSelf * self + cDu * du_s + mMain * ((m0 + m1) + m2) + mW * mw;
+                nxt = (DELTA ? T(0) : D[k * NXI + lrow]) + mSelf * self + cDu * du_s + mMain * ((m0 + m1) + m2) + mW * mw;
             }
             __syncwarp();
             if (k < N - 1 && lane < 13) DXI[lane] = nxt;
             __syncwarp();
         }
         return ok;
+    }
+
+    // ------------------------------------ predictor-corrector: correction of the step -----
+    // The corrector changes only the gradient of the QP (dg, kept in the p | d area while the sweeps do not need it);
+    // defects and Hessian are those of the affine solve, so the change of the step obeys the homogeneous recursion
+    //   dq = dg_k + J_k' dp_{k+1},  dkff_k = -Quu_k^-1 dq_u,  dp_k = dq_xi + K_k' dq_u
+    // with the gains and Quu^-1 stored by riccati_backward(): one 17-lane vector sweep, no matrix work.
+    __device__ void delta_backward()
+    {
+        T* TV = sm + L::TV;
+        const T* DG = P;                                           // [N][17], contiguous over the p | d area
+        const int zi = lane < NZ ? lane : 0;
+        const int zt = zi < 3 ? 0 : (zi == 3 ? 1 : (zi < 8 ? 2 : (zi < 11 ? 3 : (zi < 14 ? 4 : 5))));   // rate, T, uprev, pos, vel, rpy
+        const int zj = zt == 0 ? zi : (zt == 3 ? zi - 8 : (zt == 4 ? zi - 11 : (zt == 5 ? zi - 14 : 0)));
+        const int oA = zt == 1 ? JPT : (zt == 4 ? JPV + zj : (zt == 5 ? JPR + zj : 0));
+        const int sA = zt == 1 ? 1 : 3;
+        const T mA = (zt == 1 || zt == 4 || zt == 5) ? T(1) : T(0);
+        const int oB = zt == 0 ? JVW + zj : (zt == 1 ? JVT : (zt == 4 ? JVV + zj : (zt == 5 ? JVR + zj : 0)));
+        const int sB = zt == 1 ? 1 : 3;
+        const T mB = (zt == 0 || zt == 1 || zt == 4 || zt == 5) ? T(1) : T(0);
+        const T c1 = zt == 0 ? C::h : ((zt == 3 || zt == 5) ? T(1) : T(0));
+        const int i1 = zt == 0 ? 6 + zj : (zt == 3 ? zj : (zt == 5 ? 6 + zj : 0));
+        const T c2 = (zt == 0 || zt == 1) ? T(1) : T(0);
+        const int i2 = zt == 0 ? 9 + zj : 12;
+        const int xi = lane < NXI ? lane : 0;
+        const int xz = e_col(xi);
+        const bool qrow = lane >= 16 && lane < 20;
+        int uoff[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int r = lane - 16;
+            uoff[c] = qrow ? (r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r) : 13 * c + xi;
+        }
+        T pnext = T(0);
+        for (int k = N - 1; k >= 0; k--) {
+            T qz = DG[k * NZ + zi];
+            if (k < N - 1) {
+                const T* jc = JC + k * NJC;
+                if (lane < NXI) TV[lane] = pnext;
+                __syncwarp();
+                const T sa = (jc[oA] * TV[0] + jc[oA + sA] * TV[1]) + jc[oA + 2 * sA] * TV[2];
+                const T sb = (jc[oB] * TV[3] + jc[oB + sB] * TV[4]) + jc[oB + 2 * sB] * TV[5];
+                qz = (mA * sa + (c1 * TV[i1] + qz)) + (mB * sb + c2 * TV[i2]);
+            }
+            const T qu0 = __shfl_sync(0xffffffffu, qz, 0), qu1 = __shfl_sync(0xffffffffu, qz, 1);
+            const T qu2 = __shfl_sync(0xffffffffu, qz, 2), qu3 = __shfl_sync(0xffffffffu, qz, 3);
+            const T qxi = __shfl_sync(0xffffffffu, qz, xz);
+            const T* m = qrow ? QINV + k * 10 : KG + k * 52;
+            const T u4 = (m[uoff[0]] * qu0 + m[uoff[1]] * qu1) + (m[uoff[2]] * qu2 + m[uoff[3]] * qu3);
+            pnext = qxi + u4;
+            if (qrow) KFF[k * 4 + lane - 16] = -u4;
+            __syncwarp();
+        }
+        if (lane < NXI) TV[lane] = pnext;                          // dp_0 for the stage-0 solve of rollout<true>()
+        __syncwarp();
+    }
+
+    // Affine analysis and corrector right-hand side (R in shared memory, dz = affine step).  Returns the barrier
+    // target mu_t = max((mu_aff / mu)^3 mu, mu_floor); leaves dg in the p | d area, adds it to the gradient, keeps the
+    // affine step for the multiplier steps that follow (dza: this lane's flat slice; DZAP: position parts per stage).
+    __device__ T predictor_corrector_rhs(T mu, T csum, int ncomp, T mu_floor, T (&dza)[L::NT])
+    {
+        T* DG = P;
+        T pn = T(0), pd = T(1), dn = T(0), dd = T(1), S1 = T(0), S2 = T(0), S3 = T(0);
+        int t = 0;
+        for (int e = lane; e < N * NZ; e += 32, t++) {
+            const T dzi = DZ[e];
+            dza[t] = dzi;
+            if (!(e < 8 || e >= NZ)) continue;
+            const int i = e % NZ;
+            const T zi = Z[e], zl = ZL[e], zu = ZU[e];
+            const T sl = zi - BND[i], su = BND[NZ + i] - zi;
+            frac_max(pn, pd, -dzi, sl);
+            frac_max(pn, pd, dzi, su);
+            frac_max(dn, dd, zl * (sl + dzi), sl * zl);
+            frac_max(dn, dd, zu * (su - dzi), su * zu);
+            const T sdl = -zl * (dzi + sl), sdu = zu * (dzi - su);          // s_l dz_l^aff, s_u dz_u^aff
+            S1 += dzi * (zl - zu); S2 += sdl + sdu; S3 += dzi * (sdl / sl - sdu / su);
+        }
+        for (int k = lane; k < N; k += 32) {
+            const int m = live(k);
+            DZAP[k * 3] = DZ[k * NZ + 8]; DZAP[k * 3 + 1] = DZ[k * NZ + 9]; DZAP[k * 3 + 2] = DZ[k * NZ + 10];
+            for (int j = 0; j < m; j++) {
+                T r[4]; load_row(k, j, r);
+                const T sj = S[k * SS + j], lj = LC[k * SS + j];
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
+                frac_max(pn, pd, -ds, sj);
+                frac_max(dn, dd, lj * (sj + ds), sj * lj);
+                const T sdl = -lj * (ds + sj);
+                S1 += ds * lj; S2 += sdl; S3 += ds * sdl / sj;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T n2 = __shfl_xor_sync(0xffffffffu, pn, o), d2 = __shfl_xor_sync(0xffffffffu, pd, o);
+            frac_max(pn, pd, n2, d2);
+            const T n3 = __shfl_xor_sync(0xffffffffu, dn, o), d3 = __shfl_xor_sync(0xffffffffu, dd, o);
+            frac_max(dn, dd, n3, d3);
+        }
+        S1 = warp_sum(S1); S2 = warp_sum(S2); S3 = warp_sum(S3);
+        const T ap = (pn > T(0)) ? fmin(T(1), pd / pn) : T(1), ad = (dn > T(0)) ? fmin(T(1), dd / dn) : T(1);
+        const T mu_aff = (csum + ap * S1 + ad * S2 + ap * ad * S3) / (T)ncomp, sg = mu_aff / mu;
+        const T mu_t = fmax(sg * sg * sg * mu, mu_floor);
+        // corrector: dg = -(mu_t - c_l) / s_l + (mu_t - c_u) / s_u,  c = ds^aff dlambda^aff
+        t = 0;
+        for (int e = lane; e < N * NZ; e += 32, t++) {
+            T dg = T(0);
+            if (e < 8 || e >= NZ) {
+                const int i = e % NZ;
+                const T zi = Z[e], zl = ZL[e], zu = ZU[e], dzi = dza[t];
+                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                const T cl = -zl * dzi * (dzi * isl + T(1)), cu = -zu * dzi * (dzi * isu - T(1));
+                dg = (mu_t - cu) * isu - (mu_t - cl) * isl;
+            }
+            DG[e] = dg;
+            G[e] += dg;
+        }
+        __syncwarp();
+        for (int k = lane; k < N; k += 32) {
+            const int m = live(k);
+            T g0 = T(0), g1 = T(0), g2 = T(0);
+            for (int j = 0; j < m; j++) {
+                T r[4]; load_row(k, j, r);
+                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
+                const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const T ds = -rc - (r[0] * DZAP[k * 3] + r[1] * DZAP[k * 3 + 1] + r[2] * DZAP[k * 3 + 2]);
+                const T cr = -lj * ds * (ds * is + T(1));
+                const T tt = (mu_t - cr) * is;
+                g0 += r[0] * tt; g1 += r[1] * tt; g2 += r[2] * tt;
+            }
+            if (k > 0) {
+                DG[k * NZ + 8] += g0; DG[k * NZ + 9] += g1; DG[k * NZ + 10] += g2;
+                G[k * NZ + 8] += g0; G[k * NZ + 9] += g1; G[k * NZ + 10] += g2;
+            }
+        }
+        return mu_t;
     }
 
     // ------------------------------------ costates of the QP (new equality multipliers) ---
@@ -715,18 +889,28 @@ template <typename T, int N> struct Solver {
     {
         if (n * bd > bn * d) { bn = n; bd = d; }
     }
-    __device__ void step_lengths(T mu_t, T tau, T& ap_out, T& ad_out)
+    // With the predictor-corrector the multiplier steps carry the second-order terms c = ds^aff dlambda^aff
+    // (dz_l = (mu_t - c_l - z_l dz) / s_l - z_l, ...), rebuilt from the affine step (dza, DZAP); the ratios stay
+    // division-free after scaling numerator and denominator by the slack.
+    __device__ void step_lengths(T mu_t, T tau, T& ap_out, T& ad_out, const T* dza = nullptr)
     {
         T pn = T(0), pd = T(1), dn = T(0), dd = T(1);
-        for (int e = lane; e < N * NZ; e += 32) {
+        int t = 0;
+        for (int e = lane; e < N * NZ; e += 32, t++) {
             if (!(e < 8 || e >= NZ)) continue;
             const int i = e % NZ;
             const T zi = Z[e], dzi = DZ[e], zl = ZL[e], zu = ZU[e];
             const T sl = zi - BND[i], su = BND[NZ + i] - zi;
             frac_max(pn, pd, -dzi, sl);
             frac_max(pn, pd, dzi, su);
-            frac_max(dn, dd, zl * (sl + dzi) - mu_t, sl * zl);
-            frac_max(dn, dd, zu * (su - dzi) - mu_t, su * zu);
+            if (PC) {
+                const T da = dza[t];
+                frac_max(dn, dd, sl * (zl * (sl + dzi) - mu_t) - zl * da * (da + sl), sl * sl * zl);
+                frac_max(dn, dd, su * (zu * (su - dzi) - mu_t) - zu * da * (da - su), su * su * zu);
+            } else {
+                frac_max(dn, dd, zl * (sl + dzi) - mu_t, sl * zl);
+                frac_max(dn, dd, zu * (su - dzi) - mu_t, su * zu);
+            }
         }
         for (int k = lane; k < N; k += 32) {
             const int m = live(k);
@@ -736,7 +920,12 @@ template <typename T, int N> struct Solver {
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
                 frac_max(pn, pd, -ds, sj);
-                frac_max(dn, dd, lj * (sj + ds) - mu_t, sj * lj);
+                if (PC) {
+                    const T dsa = -rc - (r[0] * DZAP[k * 3] + r[1] * DZAP[k * 3 + 1] + r[2] * DZAP[k * 3 + 2]);
+                    frac_max(dn, dd, sj * (lj * (sj + ds) - mu_t) - lj * dsa * (dsa + sj), sj * sj * lj);
+                } else {
+                    frac_max(dn, dd, lj * (sj + ds) - mu_t, sj * lj);
+                }
             }
         }
 #pragma unroll
@@ -751,7 +940,7 @@ template <typename T, int N> struct Solver {
     }
 
     // --------------------------------------------------------------- accept the step ----
-    __device__ void update(T mu_t, T a, T ad)
+    __device__ void update(T mu_t, T a, T ad, const T* dza = nullptr)
     {
         for (int k = lane; k < N; k += 32) {               // corridor rows first: they read the old position
             const int m = live(k);
@@ -760,20 +949,34 @@ template <typename T, int N> struct Solver {
                 const T sj = S[k * SS + j], lj = LC[k * SS + j];
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
-                const T dl = (mu_t - lj * ds) / sj - lj;
+                T dl;
+                if (PC) {
+                    const T is = T(1) / sj;
+                    const T dsa = -rc - (r[0] * DZAP[k * 3] + r[1] * DZAP[k * 3 + 1] + r[2] * DZAP[k * 3 + 2]);
+                    const T cr = -lj * dsa * (dsa * is + T(1));
+                    dl = (mu_t - cr - lj * ds) * is - lj;
+                } else {
+                    dl = (mu_t - lj * ds) / sj - lj;
+                }
                 S[k * SS + j] = sj + a * ds;
                 LC[k * SS + j] = lj + ad * dl;
             }
         }
         __syncwarp();
-        for (int e = lane; e < N * NZ; e += 32) {
+        int t = 0;
+        for (int e = lane; e < N * NZ; e += 32, t++) {
             const T zi = Z[e], dzi = DZ[e];
             if (e < 8 || e >= NZ) {
                 const int i = e % NZ;
                 const T zl = ZL[e], zu = ZU[e];
                 const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
-                ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
-                ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
+                T cl = T(0), cu = T(0);
+                if (PC) {
+                    const T da = dza[t];
+                    cl = -zl * da * (da * isl + T(1)); cu = -zu * da * (da * isu - T(1));
+                }
+                ZL[e] = zl + ad * ((mu_t - cl - zl * dzi) * isl - zl);
+                ZU[e] = zu + ad * ((mu_t - cu + zu * dzi) * isu - zu);
             }
             Z[e] = zi + a * dzi;
         }
@@ -784,10 +987,10 @@ template <typename T, int N> struct Solver {
 // =====================================================================================
 // the kernel: grid = B CTAs of one warp; dynamic smem = Layout::bytes(mcap)
 // =====================================================================================
-template <typename T, int N>
+template <typename T, int N, bool PC = false>
 __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
 {
-    using L = Layout<T, N>;
+    using L = Layout<T, N, PC>;
     using C = Const<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
@@ -799,7 +1002,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     int* nr = reinterpret_cast<int*>(smem_raw + 16);
     T* sm = reinterpret_cast<T*>(smem_raw + L::HEAD_BYTES);
 
-    Solver<T, N> s;
+    Solver<T, N, PC> s;
     s.bind(smem_raw, lane, mcap);
     s.final_variant = (prm.variant == 1);
     T* const stg = sm + L::sh_off(mcap);   // TMA staging area = start of SH
@@ -879,11 +1082,36 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
             const T q = fmin(T(0.05) * (T(1) - xi) / xi, T(2));
             sigma = T(0.1) * q * q * q;
         }
-        const T mu_t = fmax(sigma * mu, (T)o.mu_floor);
-        s.assemble(mu_t);
-        __syncwarp();
+        T mu_t = fmax(sigma * mu, (T)o.mu_floor);
+        T dza[PC ? L::NT : 1];              // predictor-corrector: this lane's slice of the affine step
         bool ok;
-        {
+        if constexpr (PC) {
+            // Mehrotra predictor-corrector: one factorisation, two solves.  The affine solve (mu = 0) runs with the
+            // stage-phase state parked; the analysis needs that state AND must keep the gains, so the two trade
+            // places (registers <-> shared memory) around it; the corrector is a vector-only sweep.
+            s.assemble(T(0));
+            __syncwarp();
+            T parked[L::NPARK_LANE];
+            s.park(parked);
+            __syncwarp();
+            ok = s.riccati_backward();
+            ok &= s.template rollout<false>();
+            __syncwarp();
+            s.swap_parked(parked);          // state back in shared memory, gains / Quu^-1 / P_0qq into the registers
+            __syncwarp();
+            mu_t = s.predictor_corrector_rhs(mu, csum, ncomp, (T)o.mu_floor, dza);
+            __syncwarp();
+            s.swap_parked(parked);
+            __syncwarp();
+            s.delta_backward();
+            s.template rollout<true>();
+            s.costates();
+            __syncwarp();
+            s.unpark(parked);
+            __syncwarp();
+        } else {
+            s.assemble(mu_t);
+            __syncwarp();
             T parked[L::NPARK_LANE];
             s.park(parked);                 // z, z_l, z_u, y, ... leave shared memory for the sweeps
             __syncwarp();
@@ -897,7 +1125,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         if (!ok) { flag = -5; break; }
         const T tau = fmin(fmax(T(0.995), T(1) - mu), T(0.99999));
         T ap, ad;
-        s.step_lengths(mu_t, tau, ap, ad);
+        s.step_lengths(mu_t, tau, ap, ad, dza);
         // backtracking line search on (theta, barrier objective)
         const T ph0 = f_cur - mu_t * ls_cur;
         // theta below 1% of TolEq counts as feasible (also absorbs the rounding floor of theta)
@@ -917,7 +1145,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         }
         nbt_total += nbt;
         alpha_p = a; alpha_d = ad;
-        s.update(mu_t, a, ad);     // gradient / Jacobians / defects of the accepted trial stay in place
+        s.update(mu_t, a, ad, dza);     // gradient / Jacobians / defects of the accepted trial stay in place
         f_cur = ft; th_cur = tht; ls_cur = lst;
         __syncwarp();
     }

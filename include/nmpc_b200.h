@@ -54,6 +54,9 @@ typedef struct nmpc_opts {
     double s_floor;    /* floor on initial corridor slacks                   (default 1e-2)  */
     int maxit;         /* codeoptions.maxit (:56)                            200             */
     int max_bt;        /* backtracking steps per iteration                   (default 6)     */
+    int pc;            /* 1: Mehrotra predictor-corrector -- affine solve, sigma = (mu_aff/mu)^3, second-order
+                          corrector through the same factorisation (default 0; fp64 entry points only)   */
+    int reserved;
 } nmpc_opts;
 
 void nmpc_default_opts(nmpc_opts *o);

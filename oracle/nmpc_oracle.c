@@ -69,6 +69,8 @@ void nmpc_oracle_default_opts(nmpc_oracle_opts *o)
     o->s_floor = 1e-2;
     o->maxit = 200;
     o->max_bt = 6;
+    o->pc = 0;
+    o->reserved = 0;
 }
 
 /* ------------------------------------------------------------------ model ---------------- */
@@ -459,6 +461,7 @@ typedef struct {
     real zt[NS_MAX][NZ], st[NS_MAX][MC_MAX];
     real dz[NS_MAX][NZ], yn[NS_MAX][NXI], dzl[NS_MAX][NZ], dzu[NS_MAX][NZ];
     real ds[NS_MAX][MC_MAX], dlc[NS_MAX][MC_MAX];
+    real ccl[NS_MAX][NZ], ccu[NS_MAX][NZ], ccr[NS_MAX][MC_MAX];   /* predictor-corrector second-order terms */
     real Phi[NS_MAX][NZ][NZ], gt[NS_MAX][NZ], Cm[NS_MAX][NXI][NZ];
     eval_t ev[2];
 } work_t;
@@ -576,6 +579,12 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             sigma = (real)0.1 * q * q * q;
         }
         real mu_t = fmax(sigma * mu, (real)o->mu_floor);
+        /* Mehrotra predictor-corrector (o->pc): pass 0 solves with mu = 0 (affine direction), measures how far it can
+         * go (mu_aff) and sets sigma = (mu_aff / mu)^3; pass 1 solves with that target and the second-order term
+         * ds_aff * dlambda_aff in the complementarity rows (ccl / ccu / ccr).  Without pc only pass 1 runs, with zero terms. */
+        for (int k = 0; k < N; k++) { for (int i = 0; i < NZ; i++) w->ccl[k][i] = w->ccu[k][i] = 0; for (int j = 0; j < w->mcap; j++) w->ccr[k][j] = 0; }
+        for (int pass = o->pc ? 0 : 1; pass < 2 && flag == 0; pass++) {
+        const real mu_use = (pass == 0) ? (real)0 : mu_t;
         /* ---- KKT blocks */
         for (int k = 0; k < N; k++) {
             const real *hdr = w->hdr + k * 10;
@@ -585,7 +594,7 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
                 if (is_free(k, i)) {
                     real sl = w->z[k][i] - w->lb[i], su = w->ub[i] - w->z[k][i];
                     w->Phi[k][i][i] += w->zl[k][i] / sl + w->zu[k][i] / su;
-                    w->gt[k][i] = e->g[k][i] - mu_t / sl + mu_t / su;
+                    w->gt[k][i] = e->g[k][i] - (mu_use - w->ccl[k][i]) / sl + (mu_use - w->ccu[k][i]) / su;
                 } else {
                     for (int j = 0; j < NZ; j++) w->Phi[k][i][j] = w->Phi[k][j][i] = 0;
                     w->Phi[k][i][i] = 1;
@@ -595,7 +604,7 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             for (int j = 0; j < m; j++) {
                 const real *a = row(w, k, j);
                 real sg = w->lc[k][j] / w->s[k][j];
-                real tt = (mu_t + w->lc[k][j] * e->rc[k][j]) / w->s[k][j];
+                real tt = (mu_use - w->ccr[k][j] + w->lc[k][j] * e->rc[k][j]) / w->s[k][j];
                 for (int p = 0; p < 3; p++) {
                     w->gt[k][8 + p] += a[p] * tt;
                     for (int q = 0; q < 3; q++) w->Phi[k][8 + p][8 + q] += a[p] * sg * a[q];
@@ -607,6 +616,54 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             }
         }
         if (kkt_solve(N, w->Phi, w->gt, w->Cm, e->d, w->dz, w->yn)) { flag = -5; break; }
+        if (flag != 0) break;
+        if (pass == 0) {
+            real ap = 1, ad = 1;
+            for (int k = 0; k < N; k++) {
+                int m = live_rows(w, k);
+                for (int i = 0; i < NZ; i++) {
+                    if (!is_free(k, i)) continue;
+                    real sl = w->z[k][i] - w->lb[i], su = w->ub[i] - w->z[k][i], dzi = w->dz[k][i];
+                    real dl = (-w->zl[k][i] * dzi) / sl - w->zl[k][i], du = (w->zu[k][i] * dzi) / su - w->zu[k][i];
+                    if (dzi < 0) ap = fmin(ap, -sl / dzi);
+                    if (dzi > 0) ap = fmin(ap, su / dzi);
+                    if (dl < 0) ad = fmin(ad, -w->zl[k][i] / dl);
+                    if (du < 0) ad = fmin(ad, -w->zu[k][i] / du);
+                    w->ccl[k][i] = dzi * dl; w->ccu[k][i] = -dzi * du;
+                }
+                for (int j = 0; j < m; j++) {
+                    const real *a = row(w, k, j);
+                    real dsj = -e->rc[k][j] - (a[0] * w->dz[k][8] + a[1] * w->dz[k][9] + a[2] * w->dz[k][10]);
+                    real dl = (-w->lc[k][j] * dsj) / w->s[k][j] - w->lc[k][j];
+                    if (dsj < 0) ap = fmin(ap, -w->s[k][j] / dsj);
+                    if (dl < 0) ad = fmin(ad, -w->lc[k][j] / dl);
+                    w->ccr[k][j] = dsj * dl;
+                }
+            }
+            /* mu_aff = sum (s + ap ds)(lam + ad dlam) / n = (S0 + ap S1 + ad S2 + ap ad S3) / n, S3 = sum of the cc terms */
+            real S1 = 0, S2 = 0, S3 = 0;
+            for (int k = 0; k < N; k++) {
+                int m = live_rows(w, k);
+                for (int i = 0; i < NZ; i++) {
+                    if (!is_free(k, i)) continue;
+                    real sl = w->z[k][i] - w->lb[i], su = w->ub[i] - w->z[k][i], dzi = w->dz[k][i];
+                    real dl = (-w->zl[k][i] * dzi) / sl - w->zl[k][i], du = (w->zu[k][i] * dzi) / su - w->zu[k][i];
+                    S1 += dzi * w->zl[k][i] - dzi * w->zu[k][i];
+                    S2 += sl * dl + su * du;
+                    S3 += w->ccl[k][i] + w->ccu[k][i];
+                }
+                for (int j = 0; j < m; j++) {
+                    const real *a = row(w, k, j);
+                    real dsj = -e->rc[k][j] - (a[0] * w->dz[k][8] + a[1] * w->dz[k][9] + a[2] * w->dz[k][10]);
+                    real dl = (-w->lc[k][j] * dsj) / w->s[k][j] - w->lc[k][j];
+                    S1 += dsj * w->lc[k][j]; S2 += w->s[k][j] * dl; S3 += w->ccr[k][j];
+                }
+            }
+            real mu_aff = (csum + ap * S1 + ad * S2 + ap * ad * S3) / (real)ncomp, sg = mu_aff / mu;
+            mu_t = fmax(sg * sg * sg * mu, (real)o->mu_floor);
+        }
+        }
+        if (flag != 0) break;
         /* ---- multiplier / slack steps and fraction to the boundary */
         real tau = fmin(fmax((real)0.995, 1 - mu), (real)0.99999);
         real ap = 1, ad = 1;
@@ -615,8 +672,8 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             for (int i = 0; i < NZ; i++) {
                 if (!is_free(k, i)) { w->dzl[k][i] = w->dzu[k][i] = 0; continue; }
                 real sl = w->z[k][i] - w->lb[i], su = w->ub[i] - w->z[k][i], dzi = w->dz[k][i];
-                w->dzl[k][i] = (mu_t - w->zl[k][i] * dzi) / sl - w->zl[k][i];
-                w->dzu[k][i] = (mu_t + w->zu[k][i] * dzi) / su - w->zu[k][i];
+                w->dzl[k][i] = (mu_t - w->ccl[k][i] - w->zl[k][i] * dzi) / sl - w->zl[k][i];
+                w->dzu[k][i] = (mu_t - w->ccu[k][i] + w->zu[k][i] * dzi) / su - w->zu[k][i];
                 if (dzi < 0) ap = fmin(ap, -tau * sl / dzi);
                 if (dzi > 0) ap = fmin(ap, tau * su / dzi);
                 if (w->dzl[k][i] < 0) ad = fmin(ad, -tau * w->zl[k][i] / w->dzl[k][i]);
@@ -625,7 +682,7 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             for (int j = 0; j < m; j++) {
                 const real *a = row(w, k, j);
                 real dsj = -e->rc[k][j] - (a[0] * w->dz[k][8] + a[1] * w->dz[k][9] + a[2] * w->dz[k][10]);
-                real dl = (mu_t - w->lc[k][j] * dsj) / w->s[k][j] - w->lc[k][j];
+                real dl = (mu_t - w->ccr[k][j] - w->lc[k][j] * dsj) / w->s[k][j] - w->lc[k][j];
                 w->ds[k][j] = dsj;
                 w->dlc[k][j] = dl;
                 if (dsj < 0) ap = fmin(ap, -tau * w->s[k][j] / dsj);

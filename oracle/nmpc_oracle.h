@@ -41,6 +41,8 @@ typedef struct {
     double s_floor;    /* floor on initial corridor slacks                            */
     int maxit;         /* iteration cap (codeoptions.maxit 200)                       */
     int max_bt;        /* backtracking steps per iteration                            */
+    int pc;            /* 1: Mehrotra predictor-corrector (affine solve -> sigma, corrector rhs)  */
+    int reserved;
 } nmpc_oracle_opts;
 
 void nmpc_oracle_default_opts(nmpc_oracle_opts *o);

@@ -70,6 +70,21 @@ def test_gpu_matches_oracle(maker, kw):
     _compare(S.solve_host(b), O.solve_batch(b))
 
 
+@pytest.mark.parametrize("maker,kw", [(W.config2, dict(B=512)), (W.config3, dict(B=512)),
+                                      (W.config2, dict(B=128, variant=1)), (W.config4, dict(side=12, n_stages=40))])
+def test_predictor_corrector_matches_oracle(maker, kw):
+    """opts.pc = 1 (Mehrotra predictor-corrector through one factorisation), cold start with mu0 = 10: the same
+    parity bar as the default algorithm, and fewer iterations than it."""
+    b = maker(**kw)
+    g = S.solve_host(b, opts=_lib.default_opts(pc=1, mu0=10.0))
+    c = O.solve_batch(b, opts=O.default_opts(pc=1, mu0=10.0))
+    _compare(g, c)
+    base = O.solve_batch(b)
+    assert np.all(base["flag"] == 1) and g.it.mean() < 0.8 * base["it"].mean()
+    # same KKT point as the default algorithm, within the solver tolerance
+    assert np.max(np.abs(g.z - base["z"])) < 5e-3
+
+
 def test_device_pointer_api_equals_host_pointer_api():
     b = W.config2(300)
     a, c = S.solve(b), S.solve_host(b)
