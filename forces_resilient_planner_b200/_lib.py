@@ -27,7 +27,7 @@ class EllipsoidConsts(ctypes.Structure):
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
     "nmpc_default_opts", "nmpc_default_opts_f32", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
-    "nmpc_smem_bytes", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
+    "nmpc_smem_bytes", "nmpc_smem_bytes_pc", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
     "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64",
     "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_model_eval_host_f64",
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",

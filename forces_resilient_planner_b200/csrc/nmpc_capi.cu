@@ -77,7 +77,11 @@ int launch_pc(const nmpc::Params<T>& prm, cudaStream_t st)
 template <typename T, int N>
 int launch(const nmpc::Params<T>& prm, cudaStream_t st)
 {
-    return prm.o.pc ? launch_pc<T, N, true>(prm, st) : launch_pc<T, N, false>(prm, st);
+    // the predictor-corrector variant exists for the fp64 entry points (opts.pc is ignored in fp32)
+    if constexpr (sizeof(T) == 8) {
+        if (prm.o.pc) return launch_pc<T, N, true>(prm, st);
+    }
+    return launch_pc<T, N, false>(prm, st);
 }
 
 template <typename T>
@@ -388,6 +392,14 @@ long nmpc_smem_bytes(int N, int mcap, int elem_size)
     if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return -1;
     if (elem_size == 8) return N == 20 ? (long)nmpc::Layout<double, 20>::bytes(mcap) : (long)nmpc::Layout<double, 40>::bytes(mcap);
     if (elem_size == 4) return N == 20 ? (long)nmpc::Layout<float, 20>::bytes(mcap) : (long)nmpc::Layout<float, 40>::bytes(mcap);
+    return -1;
+}
+
+long nmpc_smem_bytes_pc(int N, int mcap, int elem_size)
+{
+    if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return -1;
+    if (elem_size == 8) return N == 20 ? (long)nmpc::Layout<double, 20, true>::bytes(mcap) : (long)nmpc::Layout<double, 40, true>::bytes(mcap);
+    if (elem_size == 4) return N == 20 ? (long)nmpc::Layout<float, 20, true>::bytes(mcap) : (long)nmpc::Layout<float, 40, true>::bytes(mcap);
     return -1;
 }
 

@@ -73,6 +73,7 @@ const char *nmpc_version(void);
 int nmpc_supported_horizon(int N);
 /* dynamic shared memory one problem occupies (bytes); elem_size 8 (f64) or 4 (f32) */
 long nmpc_smem_bytes(int N, int mcap, int elem_size);
+long nmpc_smem_bytes_pc(int N, int mcap, int elem_size);   /* the same for the predictor-corrector kernel (opts.pc = 1) */
 
 /* ---- device-pointer API: everything already resident in HBM, asynchronous on `stream` --------
  * z0, hdr, rows, nrows and z_out must be 16-byte aligned (TMA bulk copies / 16-byte vector loads);

@@ -72,6 +72,7 @@ def config4():
     b = W.config2(hi - lo, N, seed=W.SEED + 4 + 1000 * rank, fext=fext)
     out = {"config": f"config4: B={B} (512x512 wind sweep), N=40, sharded over {world} GPU(s), NCCL all-gather of z"}
     for name, dt, opts in (("fp64_reference_tolerances", np.float64, _lib.default_opts()),
+                           ("fp64_predictor_corrector", np.float64, _lib.default_opts(pc=1, mu0=10.0)),
                            ("fp32_stated_tolerances", np.float32, _lib.default_opts(f32=True))):
         db, res, ms = timed_solve(b, dt, opts, dev)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
