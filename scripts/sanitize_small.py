@@ -2,7 +2,7 @@
 import sys
 sys.path.insert(0, ".")
 import numpy as np, torch
-from forces_resilient_planner_b200 import workloads as W, solver as S, kkt, prep
+from forces_resilient_planner_b200 import workloads as W, solver as S, kkt, prep, _lib
 g = S.solve_host(W.config3(12))
 print("solve", g.flag.tolist(), g.it.tolist())
 g = S.solve_host(W.config4(3, 40))
@@ -21,3 +21,5 @@ cloud = t(rng.uniform([-1, -2, 0], [5, 2, 2], (200, 3))); ref = np.zeros((3, 20,
 out = prep.select_corridors(cloud, torch.tensor([200], dtype=torch.int32).cuda(), t(ref), t(np.zeros((3, 20))), E, max_polys=20, max_rows=30)
 torch.cuda.synchronize(); print("corridors ok", out[4].tolist(), out[5].tolist())
 zz = t(np.random.default_rng(2).normal(scale=3.0, size=(4, 20, 17))); prep.wrap_yaw(zz); torch.cuda.synchronize(); print("wrap ok")
+g = S.solve_host(W.config3(12), opts=_lib.default_opts(pc=1, mu0=10.0)); print("solve pc", g.flag.tolist(), g.it.tolist())
+g = S.solve_host(W.config4(3, 40), opts=_lib.default_opts(pc=1, mu0=10.0)); print("solve pc N=40", g.flag.tolist())
