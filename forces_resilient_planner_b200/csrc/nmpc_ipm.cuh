@@ -7,12 +7,14 @@
 // reference factorises an interleaved 17/13 block LDL' on one CPU thread with static storage; here
 // every problem lives in the shared memory of one warp for its entire solve:
 //
-//   * inputs (warm start, stage headers, corridor rows) arrive by TMA bulk copies
-//     (cp.async.bulk ... mbarrier::complete_tx) and the solution leaves by a bulk store;
+//   * inputs (warm start, stage headers, row counts) arrive by TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) and the solution leaves by a bulk store; the
+//     read-only corridor rows are read through L1 (LDG.128) where they are used;
 //   * "lanes = stages" phases (model evaluation, barrier terms, residual norms, step-to-boundary,
 //     line-search merit) run one stage per lane and finish with warp-shuffle reductions;
-//   * the KKT system is solved by a Riccati recursion over xi = [x(9); u_prev(4)] whose 13x13 /
-//     9x13 / 4x13 products are spread over the 32 lanes ("lanes = matrix entries"), the 4x4
+//   * the KKT system is solved by a Riccati recursion over xi = [x(9); u_prev(4)]: the products with
+//     the structured dynamics Jacobian run one row / column per lane with the Jacobian words
+//     broadcast, the rank-4 update of the cost-to-go with "lanes = matrix entries", the 4x4
 //     pivot block being factorised redundantly in registers;
 //   * the iteration loop, convergence test and exit code are per warp, so a slow or diverging
 //     instance never stalls another one.
@@ -23,6 +25,9 @@
 // fraction-to-boundary tau = min(max(0.995, 1-mu), 0.99999), backtracking on
 // (theta, barrier objective), termination on the reference tolerances (1e-4 inf-norms,
 // matlab_code/mpc/normal/mpc_generator_normal.m:76-79), iteration cap 200 (:56).
+// Option (template parameter PC, opts.pc): Mehrotra predictor-corrector through one factorisation --
+// affine solve, sigma = (mu_aff / mu)^3, second-order terms, corrector as a vector-only sweep
+// (delta_backward / rollout<true>) with the stored gains and Quu^-1.
 #pragma once
 #include <cstdint>
 #include "nmpc_model.cuh"
