@@ -59,6 +59,25 @@ def test_random_configs_converge_and_pass_reference_kkt(maker, kw):
         assert abs(res[0] - r["info_real"][i, 2]) < 1e-6 and abs(res[1] - r["info_real"][i, 0]) < 1e-7
 
 
+@pytest.mark.parametrize("maker,kw", [(W.config2, dict(B=96)), (W.config3, dict(B=96)),
+                                      (W.config2, dict(B=48, variant=1)), (W.config4, dict(side=8, n_stages=40))])
+def test_predictor_corrector_option_reaches_the_same_kkt_points(maker, kw):
+    """opts.pc = 1 (Mehrotra predictor-corrector): every point still passes ForcesPro's acceptance test when
+    re-evaluated with the reference callbacks, it is the point the default algorithm finds, and it takes
+    markedly fewer iterations."""
+    b = maker(**kw)
+    r = O.solve_batch(b, opts=O.default_opts(pc=1, mu0=10.0), multipliers=True)
+    base = O.solve_batch(b)
+    assert np.all(r["flag"] == 1) and np.all(base["flag"] == 1)
+    assert r["it"].mean() < 0.8 * base["it"].mean() and r["it"].max() <= base["it"].max() + 4
+    assert np.max(np.abs(r["z"] - base["z"])) < 5e-3
+    if b.N == 20:
+        model = _model(b.variant)
+        for i in range(0, b.B, 8):
+            res = H.kkt_residuals(b, i, r["z"][i], r["y"][i], r["zl"][i], r["zu"][i], r["lc"][i], model)
+            assert max(res) <= TOL, (i, res)
+
+
 def test_long_horizon_config4_converges():
     b = W.config4(8, 40)
     r = O.solve_batch(b)
