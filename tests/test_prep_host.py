@@ -152,3 +152,19 @@ def test_corridor_restatement_properties():
     # an obstacle within the 5 cm seed sphere shrinks the ellipsoid instead of being swallowed
     C, d = CN.find_ellipsoid(p1, p2, [np.array([1.05, 2.03, 1.0])])
     assert np.linalg.norm(np.linalg.inv(C) @ (np.array([1.05, 2.03, 1.0]) - d)) >= 1 - 1e-9
+
+
+def test_corridor_restatement_degenerate_seeds():
+    """Edge cases of add_local_bbox / vec3_to_rotation: a vertical seed segment (no horizontal direction: the
+    reference falls back to dir_h = (-1, 0, 0)) and obstacle points exactly on a box face (kept, non-exclusive)."""
+    from oracle import corridor_np as CN
+    p1 = np.array([0.0, 0.0, 1.0]); p2 = np.array([0.0, 0.0, 1.1])
+    planes = CN.local_bbox_planes(p1, p2, (2.0, 2.0, 1.0))
+    normals = np.array([n for _, n in planes])
+    assert np.allclose(normals[0], [-1, 0, 0]) and np.allclose(normals[2], [0, 0, 1])
+    assert np.allclose(np.abs(np.linalg.det(np.stack([normals[0], normals[2], normals[4]]))), 1.0)   # orthonormal frame
+    A, b = CN.dilate_segment(p1, p2, np.array([[0.5, 0.0, 1.05], [2.0, 0.0, 1.05], [2.0 + 1e-6, 0.0, 1.05]]))
+    assert A.shape[0] == 7                                   # the first point carves; the one on the face is behind that plane; the one outside is ignored
+    assert np.all(A @ ((p1 + p2) / 2) - b < 0)
+    R = CN.vec3_to_rotation(np.array([0.0, 0.0, 0.1]))
+    assert np.allclose(R @ np.array([1.0, 0.0, 0.0]), [0.0, 0.0, 1.0])      # the ellipsoid's long axis follows the segment
