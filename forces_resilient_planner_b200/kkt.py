@@ -34,7 +34,8 @@ def _check(rc):
 
 
 def riccati_factor(phi, jc, stream=None):
-    """phi [B,N,21], jc [B,N,51] (cuda tensors) -> fac [B,N,204], status [B] (int32)."""
+    """phi [B,N,21], jc [B,N,51] (cuda tensors) -> fac [B,N,204] (opaque: N*204 words per problem, see
+    include/nmpc_b200.h), status [B] (int32)."""
     import torch
     lib = _lib.load()
     B, N, _ = phi.shape
@@ -50,7 +51,7 @@ def riccati_factor(phi, jc, stream=None):
 
 
 def kkt_backsolve(fac, g, d, dz=None, y=None, stream=None):
-    """fac [B,N,204], g [B,N,17], d [B,N,13] -> dz [B,N,17], y [B,N,13]."""
+    """fac [B,N,204] (as produced by riccati_factor), g [B,N,17], d [B,N,13] -> dz [B,N,17], y [B,N,13]."""
     import torch
     lib = _lib.load()
     B, N, _ = fac.shape

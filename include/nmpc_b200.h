@@ -119,7 +119,9 @@ int nmpc_solve_batch_host_f32(int B, int N, int mcap, const float *xinit, const 
  * f_17_ldl_forward_solve_rm / f_13_backward_solve_rm) for the Riccati factor:
  *   phi [B][N][21]  stage Hessian, compact: diag(17) | pos block off-diag (01,02,12) | H[u_i][uprev_i]
  *   jc  [B][N][51]  compact dynamics Jacobian (pos+/vel+ wrt vel, rpy, thrust; vel+ wrt rates)
- *   fac [B][N][nmpc_backsolve_factor_words()]   P_k packed 91 | K_k 52 | Quu^-1 packed 10 | J_k 51
+ *   fac [B][N * nmpc_backsolve_factor_words()]  opaque to the caller; per problem two regions so that each can be
+ *       fetched on its own: [P: N x 91, symmetric 13x13 in a bank-conflict-free packed layout]
+ *       [N x 113: K_k 52 | Quu^-1 packed 10 | J_k 51].  All pointers 16-byte aligned.
  *   g   [B][N][17], d [B][N][13] (c-ordering, row N-1 unused)  ->  dz [B][N][17], y [B][N][13]
  * solving   min 1/2 dz'Phi dz + g'dz  s.t.  E dz_{k+1} = J_k dz_k + d_k,  dz_0[8:17] = 0.         */
 int nmpc_backsolve_factor_words(void);
