@@ -16,7 +16,7 @@ class NmpcOpts(ctypes.Structure):
                 ("tol_stat", ctypes.c_double), ("tol_eq", ctypes.c_double),
                 ("tol_ineq", ctypes.c_double), ("tol_comp", ctypes.c_double),
                 ("kappa_push", ctypes.c_double), ("s_floor", ctypes.c_double),
-                ("maxit", ctypes.c_int), ("max_bt", ctypes.c_int), ("pc", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("maxit", ctypes.c_int), ("max_bt", ctypes.c_int), ("pc", ctypes.c_int), ("mixed", ctypes.c_int)]
 
 
 class EllipsoidConsts(ctypes.Structure):
@@ -26,10 +26,10 @@ class EllipsoidConsts(ctypes.Structure):
 
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
-    "nmpc_default_opts", "nmpc_default_opts_f32", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
+    "nmpc_default_opts", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
     "nmpc_smem_bytes", "nmpc_smem_bytes_pc", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
-    "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64",
-    "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_model_eval_host_f64",
+    "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64", "nmpc_solve_batch_mixed_f64",
+    "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_solve_batch_host_mixed_f64", "nmpc_model_eval_host_f64",
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",
     "nmpc_backsolve_algorithmic_bytes",
@@ -60,9 +60,13 @@ def load() -> ctypes.CDLL:
     for name in ("nmpc_solve_batch_f64", "nmpc_solve_batch_f32"):
         getattr(lib, name).argtypes = sig + [_vp]
         getattr(lib, name).restype = _i
-    for name in ("nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32"):
+    for name in ("nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_solve_batch_host_mixed_f64"):
         getattr(lib, name).argtypes = sig
         getattr(lib, name).restype = _i
+    lib.nmpc_solve_batch_ex_f64.argtypes = sig + [_vp] * 5
+    lib.nmpc_solve_batch_ex_f64.restype = _i
+    lib.nmpc_solve_batch_mixed_f64.argtypes = sig + [_vp] * 6
+    lib.nmpc_solve_batch_mixed_f64.restype = _i
     _lib = lib
     return lib
 
@@ -71,9 +75,10 @@ def last_error() -> str:
     return load().nmpc_last_error().decode()
 
 
-def default_opts(f32: bool = False, **kw) -> NmpcOpts:
+def default_opts(**kw) -> NmpcOpts:
+    """nmpc_default_opts: the reference tolerances (1e-4), for the fp64 and the mixed-precision entry points alike."""
     o = NmpcOpts()
-    (load().nmpc_default_opts_f32 if f32 else load().nmpc_default_opts)(ctypes.byref(o))
+    load().nmpc_default_opts(ctypes.byref(o))
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(f"nmpc_opts has no field {k!r}")

@@ -4,6 +4,7 @@ The shared object is git-ignored but travels to the GPU box with the gpurun snap
 """
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -12,9 +13,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libnmpc_b200.so")
 SOURCES = ["nmpc_capi.cu"]
-HEADERS = ["nmpc_ipm.cuh", "nmpc_model.cuh", "nmpc_backsolve.cuh", "nmpc_prep.cuh",
-           "../../include/nmpc_b200.h", "../../include/FORCESNLPsolver_normal.h",
-           "../../include/FORCESNLPsolver_final.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
@@ -30,8 +28,10 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    # every kernel header and every public header the translation unit includes
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

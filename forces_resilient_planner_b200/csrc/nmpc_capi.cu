@@ -23,6 +23,7 @@
 #include "nmpc_corridor.cuh"
 #include "nmpc_ellipsoid.cuh"
 #include "nmpc_ipm.cuh"
+#include "nmpc_ipm_mixed.cuh"
 #include "nmpc_prep.cuh"
 
 // ---- the ABI contract of the reference headers --------------------------------
@@ -39,6 +40,7 @@ static_assert(offsetof(FORCESNLPsolver_normal_info, solvetime) == 120, "solvetim
 static_assert(sizeof(FORCESNLPsolver_final_params) == 23600 && sizeof(FORCESNLPsolver_final_output) == 2720 &&
                   sizeof(FORCESNLPsolver_final_info) == 136, "final ABI");
 static_assert(sizeof(nmpc_opts) == sizeof(nmpc::Opts), "opts mirror");
+static_assert(offsetof(nmpc_opts, mixed) == offsetof(nmpc::Opts, mixed), "opts mirror");
 
 namespace {
 
@@ -60,16 +62,29 @@ int fail(int code, const char* fmt, ...)
             return fail(NMPC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));     \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember the largest
+// value configured per (kernel, device), so that a thread which solves on cuda:0 and then on cuda:1 configures both.
+constexpr int kMaxDevices = 64;
+template <typename K>
+int ensure_smem(K kernel, size_t smem, size_t (&configured)[kMaxDevices])
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(NMPC_ERR_CUDA, "device ordinal %d out of range", dev);
+    if (smem > configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    return 0;
+}
+
 template <typename T, int N, bool PC>
 int launch_pc(const nmpc::Params<T>& prm, cudaStream_t st)
 {
     using L = nmpc::Layout<T, N, PC>;
     const size_t smem = L::bytes(prm.mcap);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::nmpc_ipm_kernel<T, N, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_smem(nmpc::nmpc_ipm_kernel<T, N, PC>, smem, configured)) return rc;
     nmpc::nmpc_ipm_kernel<T, N, PC><<<prm.B, 32, smem, st>>>(prm);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -77,18 +92,31 @@ int launch_pc(const nmpc::Params<T>& prm, cudaStream_t st)
 template <typename T, int N>
 int launch(const nmpc::Params<T>& prm, cudaStream_t st)
 {
-    // the predictor-corrector variant exists for the fp64 entry points (opts.pc is ignored in fp32)
-    if constexpr (sizeof(T) == 8) {
-        if (prm.o.pc) return launch_pc<T, N, true>(prm, st);
-    }
+    if (prm.o.pc) return launch_pc<T, N, true>(prm, st);
     return launch_pc<T, N, false>(prm, st);
 }
+template <int N>
+int launch_mixed(const nmpc::MixedParams& prm, cudaStream_t st)
+{
+    const size_t smem = nmpc::MLayout<N>::bytes(prm.mcap);
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_smem(nmpc::nmpc_ipm_mixed_kernel<N>, smem, configured)) return rc;
+    nmpc::nmpc_ipm_mixed_kernel<N><<<prm.B, 32, smem, st>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
-template <typename T>
-int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr, const T* rows,
-                 const int* nrows, int variant, const nmpc_opts* opts, T* z_out, int* info_int,
-                 T* info_real, void* stream, T* y_out = nullptr, T* zl_out = nullptr, T* zu_out = nullptr,
-                 T* lc_out = nullptr, const int* order = nullptr)
+// order[0 .. *count) <- the problems whose exit flag is not 1 (optimal); one pass, order of arrival
+__global__ void collect_unsolved_kernel(int B, const int* info_int, int* count, int* order)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && info_int[(size_t)b * 4] != 1) order[atomicAdd(count, 1)] = b;
+}
+
+// argument checks shared by the fp64 and the mixed-precision device entry points
+int check_solve_args(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+                     const int* nrows, int variant, const nmpc_opts* opts, const void* z_out, const int* info_int,
+                     const void* info_real, nmpc_opts* o)
 {
     if (B < 0 || mcap < 0 || mcap > 32 || (variant != 0 && variant != 1))
         return fail(NMPC_ERR_ARG, "bad argument: B=%d mcap=%d variant=%d", B, mcap, variant);
@@ -97,31 +125,74 @@ int solve_device(int B, int N, int mcap, const T* xinit, const T* z0, const T* h
     if (!xinit || !z0 || !hdr || !nrows || !z_out || !info_int || !info_real || (mcap > 0 && !rows))
         return fail(NMPC_ERR_ARG, "null pointer argument");
     // the per-problem blocks are moved by TMA bulk copies / 16-byte vector loads
-    for (const void* p : {(const void*)z0, (const void*)hdr, (const void*)rows, (const void*)nrows, (const void*)z_out})
+    for (const void* p : {z0, hdr, rows, (const void*)nrows, z_out})
         if (reinterpret_cast<uintptr_t>(p) & 15) return fail(NMPC_ERR_ARG, "device pointers must be 16-byte aligned");
-    nmpc::Params<T> prm;
-    prm.B = B; prm.mcap = mcap; prm.variant = variant;
+    if (opts) *o = *opts; else nmpc_default_opts(o);
+    if (!(o->mu0 > 0) || !(o->mu_floor > 0) || o->maxit < 0 || o->max_bt < 0)
+        return fail(NMPC_ERR_ARG, "bad solver options");
+    return 0;
+}
+
+// fp64 kernel.  io32: the arrays are float (re-solve of mixed-precision failures); count: device counter of live `order` entries
+int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+                 const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int,
+                 void* info_real, void* stream, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
+                 void* lc_out = nullptr, const int* order = nullptr, const int* count = nullptr, int io32 = 0)
+{
+    nmpc_opts o;
+    if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
+    if (B == 0) return 0;
+    nmpc::Params<double> prm;
+    prm.B = B; prm.mcap = mcap; prm.variant = variant; prm.io32 = io32;
+    prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order; prm.count = count;
+    prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
+    prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
+    std::memcpy(&prm.o, &o, sizeof(o));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return N == 20 ? launch<double, 20>(prm, st) : launch<double, 40>(prm, st);
+}
+
+// Mixed-precision solve (nmpc_ipm_mixed.cuh) followed, on the same stream and without a host round trip, by the
+// fp64 re-solve of whatever it did not bring to exit flag 1: single precision loses the cost-to-go's positive
+// definiteness on rare, badly scaled instances (flag -5) or stalls (flag 0 after MIXED_BAIL_IT iterations).
+// The list of those problems is built on the device; the fp64 grid is launched at full width and the CTAs beyond
+// the list exit at once.  Re-solved problems carry info_int[b][3] = 1.
+int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+                const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int, void* info_real,
+                void* stream, int io32, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
+                void* lc_out = nullptr, const int* order = nullptr)
+{
+    nmpc_opts o;
+    if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
+    if (B == 0) return 0;
+    nmpc::MixedParams prm;
+    prm.B = B; prm.mcap = mcap; prm.variant = variant; prm.io32 = io32;
     prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order;
     prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
-    nmpc_opts o;
-    if (opts) o = *opts; else nmpc_default_opts(&o);
-    if (!(o.mu0 > 0) || !(o.mu_floor > 0) || o.maxit < 0 || o.max_bt < 0)
-        return fail(NMPC_ERR_ARG, "bad solver options");
     std::memcpy(&prm.o, &o, sizeof(o));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return N == 20 ? launch<T, 20>(prm, st) : launch<T, 40>(prm, st);
+    if (int rc = (N == 20 ? launch_mixed<20>(prm, st) : launch_mixed<40>(prm, st))) return rc;
+    if (o.mixed < 0) return 0;                      // opts.mixed = -1: no fp64 safety net (tests, profiling)
+    int* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), ((size_t)B + 4) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(ws, 0, 4 * sizeof(int), st));
+    collect_unsolved_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, info_int, ws, ws + 4);
+    CUDA_TRY(cudaGetLastError());
+    nmpc_opts o64 = o;
+    o64.pc = 0;
+    int rc = solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, &o64, z_out, info_int, info_real, stream,
+                          y_out, zl_out, zu_out, lc_out, ws + 4, ws, io32);
+    CUDA_TRY(cudaFreeAsync(ws, st));
+    return rc;
 }
 
 template <typename T, int N>
 int launch_factor(const nmpc::FactorParams<T>& q, cudaStream_t st)
 {
     const size_t smem = nmpc::Layout<T, N>::bytes(0);
-    static thread_local bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::riccati_factor_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_smem(nmpc::riccati_factor_kernel<T, N>, smem, configured)) return rc;
     nmpc::riccati_factor_kernel<T, N><<<q.B, 32, smem, st>>>(q);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -130,11 +201,8 @@ template <typename T, int N>
 int launch_backsolve(const nmpc::BacksolveParams<T>& q, cudaStream_t st)
 {
     const size_t smem = nmpc::BsLayout<T, N>::bytes();
-    static thread_local bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::kkt_backsolve_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_smem(nmpc::kkt_backsolve_kernel<T, N>, smem, configured)) return rc;
     nmpc::kkt_backsolve_kernel<T, N><<<q.B, 32, smem, st>>>(q);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -162,7 +230,7 @@ int backsolve_device(int B, int N, const T* fac, const T* g, const T* d, T* dz, 
     return N == 20 ? launch_backsolve<T, 20>(q, st) : launch_backsolve<T, 40>(q, st);
 }
 
-// grow-only device arena for the host-pointer API and the FORCES shim
+// grow-only device arena for the host-pointer API and the FORCES shim; one arena and one set of streams per device
 struct Arena {
     void* p = nullptr;
     size_t cap = 0;
@@ -176,57 +244,87 @@ struct Arena {
         return 0;
     }
 };
-std::mutex g_host_mutex;   // the reference solver is non-reentrant (static workspace); mirror that
-Arena g_arena;
 constexpr int kHostStreams = 3;
-cudaStream_t g_streams[kHostStreams] = {nullptr, nullptr, nullptr};
+struct HostCtx {
+    Arena arena;
+    cudaStream_t streams[kHostStreams] = {nullptr, nullptr, nullptr};
+};
+std::mutex g_host_mutex;   // the reference solver is non-reentrant (static workspace); mirror that
+HostCtx g_host[kMaxDevices];
 
 inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
-template <typename T>
-int solve_host(int B, int N, int mcap, const T* xinit, const T* z0, const T* hdr, const T* rows,
-               const int* nrows, int variant, const nmpc_opts* opts, T* z_out, int* info_int, T* info_real)
+// Host buffers in, host buffers out.  esz = 8: double arrays, fp64 kernel (mixed = false) or mixed-precision kernel;
+// esz = 4: float arrays, mixed-precision kernel.
+int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+               const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int, void* info_real,
+               size_t esz, bool mixed)
 {
     if (B < 0) return fail(NMPC_ERR_ARG, "B < 0");
     if (B == 0) return 0;
     if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return fail(NMPC_ERR_ARG, "bad N=%d or mcap=%d", N, mcap);
     std::lock_guard<std::mutex> lock(g_host_mutex);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(NMPC_ERR_CUDA, "device ordinal %d out of range", dev);
+    HostCtx& ctx = g_host[dev];
     for (int i = 0; i < kHostStreams; i++)
-        if (!g_streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
-    const size_t n_x = (size_t)B * 9 * sizeof(T), n_z = (size_t)B * N * 17 * sizeof(T);
-    const size_t n_h = (size_t)B * N * 10 * sizeof(T), n_r = (size_t)B * N * mcap * 4 * sizeof(T);
-    const size_t n_n = (size_t)B * N * sizeof(int), n_ii = (size_t)B * 4 * sizeof(int), n_ir = (size_t)B * 8 * sizeof(T);
+        if (!ctx.streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx.streams[i], cudaStreamNonBlocking));
+    const size_t n_x = (size_t)B * 9 * esz, n_z = (size_t)B * N * 17 * esz;
+    const size_t n_h = (size_t)B * N * 10 * esz, n_r = (size_t)B * N * mcap * 4 * esz;
+    const size_t n_n = (size_t)B * N * sizeof(int), n_ii = (size_t)B * 4 * sizeof(int), n_ir = (size_t)B * 8 * esz;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off += align256(n ? n : 1); return o; };
     const size_t o_x = take(n_x), o_z = take(n_z), o_h = take(n_h), o_r = take(n_r), o_n = take(n_n);
     const size_t o_zo = take(n_z), o_ii = take(n_ii), o_ir = take(n_ir);
-    if (int rc = g_arena.reserve(off)) return rc;
-    char* base = static_cast<char*>(g_arena.p);
+    if (int rc = ctx.arena.reserve(off)) return rc;
+    char* base = static_cast<char*>(ctx.arena.p);
+    const char *hx = static_cast<const char*>(xinit), *hz = static_cast<const char*>(z0), *hh = static_cast<const char*>(hdr),
+               *hr = static_cast<const char*>(rows);
+    char *hzo = static_cast<char*>(z_out), *hir = static_cast<char*>(info_real);
     // Large batches are cut into chunks that round-robin over a few streams: the H2D copy of chunk
     // i+1 and the D2H copy of chunk i-1 overlap the solve of chunk i, and the next chunk's CTAs fill
-    // the tail wave of the previous kernel.  Chunk boundaries are multiples of 2 problems, so every
-    // per-problem block keeps the 16-byte alignment the TMA copies need.
+    // the tail wave of the previous kernel.  Chunk boundaries are multiples of 4 problems, so every
+    // per-problem block keeps the 16-byte alignment the TMA copies need (fp32 and fp64).
     const int n_chunks = B >= 2048 ? 4 : 1;
-    const int per = ((B + n_chunks - 1) / n_chunks + 1) & ~1;
-    for (int c = 0, lo = 0; lo < B; c++, lo += per) {
-        const int nb = (B - lo < per) ? B - lo : per;
-        cudaStream_t st = g_streams[c % kHostStreams];
-        const size_t pz = (size_t)N * 17 * sizeof(T), ph = (size_t)N * 10 * sizeof(T), pr = (size_t)N * mcap * 4 * sizeof(T);
-        CUDA_TRY(cudaMemcpyAsync(base + o_x + (size_t)lo * 9 * sizeof(T), xinit + (size_t)lo * 9, (size_t)nb * 9 * sizeof(T), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(base + o_z + lo * pz, z0 + (size_t)lo * N * 17, nb * pz, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(base + o_h + lo * ph, hdr + (size_t)lo * N * 10, nb * ph, cudaMemcpyHostToDevice, st));
-        if (pr) CUDA_TRY(cudaMemcpyAsync(base + o_r + lo * pr, rows + (size_t)lo * N * mcap * 4, nb * pr, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(base + o_n + (size_t)lo * N * sizeof(int), nrows + (size_t)lo * N, (size_t)nb * N * sizeof(int), cudaMemcpyHostToDevice, st));
-        int rc = solve_device<T>(nb, N, mcap, (const T*)(base + o_x) + (size_t)lo * 9, (const T*)(base + o_z) + (size_t)lo * N * 17,
-                                 (const T*)(base + o_h) + (size_t)lo * N * 10, (const T*)(base + o_r) + (size_t)lo * N * mcap * 4,
-                                 (const int*)(base + o_n) + (size_t)lo * N, variant, opts, (T*)(base + o_zo) + (size_t)lo * N * 17,
-                                 (int*)(base + o_ii) + (size_t)lo * 4, (T*)(base + o_ir) + (size_t)lo * 8, st);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(z_out + (size_t)lo * N * 17, base + o_zo + lo * pz, nb * pz, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(info_int + (size_t)lo * 4, base + o_ii + (size_t)lo * 4 * sizeof(int), (size_t)nb * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(info_real + (size_t)lo * 8, base + o_ir + (size_t)lo * 8 * sizeof(T), (size_t)nb * 8 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    const int per = ((B + n_chunks - 1) / n_chunks + 3) & ~3;
+    auto enqueue = [&]() -> int {
+        for (int c = 0, lo = 0; lo < B; c++, lo += per) {
+            const int nb = (B - lo < per) ? B - lo : per;
+            cudaStream_t st = ctx.streams[c % kHostStreams];
+            const size_t px = 9 * esz, pz = (size_t)N * 17 * esz, ph = (size_t)N * 10 * esz, pr = (size_t)N * mcap * 4 * esz;
+            const size_t pn = (size_t)N * sizeof(int), pii = 4 * sizeof(int), pir = 8 * esz;
+            CUDA_TRY(cudaMemcpyAsync(base + o_x + lo * px, hx + lo * px, nb * px, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(base + o_z + lo * pz, hz + lo * pz, nb * pz, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(base + o_h + lo * ph, hh + lo * ph, nb * ph, cudaMemcpyHostToDevice, st));
+            if (pr) CUDA_TRY(cudaMemcpyAsync(base + o_r + lo * pr, hr + lo * pr, nb * pr, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(base + o_n + lo * pn, nrows + (size_t)lo * N, nb * pn, cudaMemcpyHostToDevice, st));
+            int* d_ii = reinterpret_cast<int*>(base + o_ii + lo * pii);
+            int rc;
+            if (mixed)
+                rc = solve_mixed(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
+                                 reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
+                                 base + o_ir + lo * pir, st, esz == 4);
+            else
+                rc = solve_device(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
+                                  reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
+                                  base + o_ir + lo * pir, st);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(hzo + lo * pz, base + o_zo + lo * pz, nb * pz, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(info_int + (size_t)lo * 4, d_ii, nb * pii, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(hir + lo * pir, base + o_ir + lo * pir, nb * pir, cudaMemcpyDeviceToHost, st));
+        }
+        return 0;
+    };
+    const int rc = enqueue();
+    // also on failure: nothing may still be in flight into the shared arena (or the caller's buffers) when we return
+    cudaError_t serr = cudaSuccess;
+    for (int i = 0; i < kHostStreams; i++) {
+        const cudaError_t e = cudaStreamSynchronize(ctx.streams[i]);
+        if (e != cudaSuccess && serr == cudaSuccess) serr = e;
     }
-    for (int i = 0; i < kHostStreams; i++) CUDA_TRY(cudaStreamSynchronize(g_streams[i]));
+    if (rc) return rc;
+    if (serr != cudaSuccess) return fail(NMPC_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(serr));
     return 0;
 }
 
@@ -263,8 +361,8 @@ int forces_solve(const double* xinit, const double* x0, const double* allp, doub
         }
     }
     int ii[4] = {0, 0, 0, 0};
-    int rc = solve_host<double>(1, N, mcap, xinit, x0, hdr.data(), rows.data(), nrows.data(), variant, nullptr,
-                                out340, ii, ir);
+    int rc = solve_host(1, N, mcap, xinit, x0, hdr.data(), rows.data(), nrows.data(), variant, nullptr,
+                        out340, ii, ir, sizeof(double), false);
     *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) return rc == NMPC_ERR_ARG ? -11 : rc;
     *it = ii[1]; *nbt = ii[2];
@@ -372,75 +470,79 @@ void nmpc_default_opts(nmpc_opts* o)
     o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-4;
     o->kappa_push = 1e-2; o->s_floor = 1e-2;
     o->maxit = 200; o->max_bt = 6;
-    o->pc = 0; o->reserved = 0;
-}
-
-void nmpc_default_opts_f32(nmpc_opts* o)
-{
-    // what single precision can resolve on this problem (gradients of order 1e2..1e3, slacks that are
-    // differences of O(1) numbers): stationarity 2e-2, complementarity 1e-2 with the barrier held at 1e-3
-    nmpc_default_opts(o);
-    o->tol_stat = 2e-2; o->tol_comp = 1e-2; o->mu_floor = 1e-3;
+    o->pc = 0; o->mixed = 0;
 }
 
 const char* nmpc_last_error(void) { return g_err; }
-const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a; fused warp-per-problem IPM)"; }
+const char* nmpc_version(void) { return "nmpc_b200 0.2 (sm_100a; fused warp-per-problem IPM, fp64 and mixed precision)"; }
 int nmpc_supported_horizon(int N) { return N == 20 || N == 40; }
 
 long nmpc_smem_bytes(int N, int mcap, int elem_size)
 {
     if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return -1;
     if (elem_size == 8) return N == 20 ? (long)nmpc::Layout<double, 20>::bytes(mcap) : (long)nmpc::Layout<double, 40>::bytes(mcap);
-    if (elem_size == 4) return N == 20 ? (long)nmpc::Layout<float, 20>::bytes(mcap) : (long)nmpc::Layout<float, 40>::bytes(mcap);
+    if (elem_size == 4) return N == 20 ? (long)nmpc::MLayout<20>::bytes(mcap) : (long)nmpc::MLayout<40>::bytes(mcap);
     return -1;
 }
 
 long nmpc_smem_bytes_pc(int N, int mcap, int elem_size)
 {
-    if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32) return -1;
-    if (elem_size == 8) return N == 20 ? (long)nmpc::Layout<double, 20, true>::bytes(mcap) : (long)nmpc::Layout<double, 40, true>::bytes(mcap);
-    if (elem_size == 4) return N == 20 ? (long)nmpc::Layout<float, 20, true>::bytes(mcap) : (long)nmpc::Layout<float, 40, true>::bytes(mcap);
-    return -1;
+    if (!nmpc_supported_horizon(N) || mcap < 0 || mcap > 32 || elem_size != 8) return -1;
+    return N == 20 ? (long)nmpc::Layout<double, 20, true>::bytes(mcap) : (long)nmpc::Layout<double, 40, true>::bytes(mcap);
 }
 
 int nmpc_solve_batch_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                          const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
                          int* info_int, double* info_real, void* cuda_stream)
 {
-    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream);
+    return solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream);
 }
 int nmpc_solve_batch_f32(int B, int N, int mcap, const float* xinit, const float* z0, const float* hdr,
                          const float* rows, const int* nrows, int variant, const nmpc_opts* opts, float* z_out,
                          int* info_int, float* info_real, void* cuda_stream)
 {
-    return solve_device<float>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream);
+    return solve_mixed(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream, 1);
+}
+int nmpc_solve_batch_mixed_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                               const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
+                               int* info_int, double* info_real, double* y_out, double* zl_out, double* zu_out,
+                               double* lc_out, const int* order, void* cuda_stream)
+{
+    return solve_mixed(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream, 0,
+                       y_out, zl_out, zu_out, lc_out, order);
 }
 int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                             const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
                             int* info_int, double* info_real, double* y_out, double* zl_out, double* zu_out,
                             double* lc_out, void* cuda_stream)
 {
-    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
-                                cuda_stream, y_out, zl_out, zu_out, lc_out);
+    return solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
+                        cuda_stream, y_out, zl_out, zu_out, lc_out);
 }
 int nmpc_solve_batch_ordered_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                                  const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
                                  int* info_int, double* info_real, const int* order, void* cuda_stream)
 {
-    return solve_device<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
-                                cuda_stream, nullptr, nullptr, nullptr, nullptr, order);
+    return solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real,
+                        cuda_stream, nullptr, nullptr, nullptr, nullptr, order);
 }
 int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                               const double* rows, const int* nrows, int variant, const nmpc_opts* opts,
                               double* z_out, int* info_int, double* info_real)
 {
-    return solve_host<double>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real);
+    return solve_host(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, 8, false);
 }
 int nmpc_solve_batch_host_f32(int B, int N, int mcap, const float* xinit, const float* z0, const float* hdr,
                               const float* rows, const int* nrows, int variant, const nmpc_opts* opts,
                               float* z_out, int* info_int, float* info_real)
 {
-    return solve_host<float>(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real);
+    return solve_host(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, 4, true);
+}
+int nmpc_solve_batch_host_mixed_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                                    const double* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                                    double* z_out, int* info_int, double* info_real)
+{
+    return solve_host(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, 8, true);
 }
 
 int nmpc_backsolve_factor_words(void) { return nmpc::FAC_WORDS; }
@@ -493,11 +595,9 @@ int nmpc_select_corridors_f64(int B, int N, int M, int P, int R, const double* c
         return fail(NMPC_ERR_ARG, "null pointer argument");
     const size_t smem = ((size_t)(M + 15) & ~(size_t)15) + (size_t)R * 4 * sizeof(double);
     if (smem > 200 * 1024) return fail(NMPC_ERR_ARG, "cloud too large for the per-agent flag array: M=%d", M);
-    static thread_local size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::corridor_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (smem > 48 * 1024)
+        if (int rc = ensure_smem(nmpc::corridor_select_kernel, smem, configured)) return rc;
     nmpc::CorridorParams q{B, N, M, P, R, cloud, cloud_stride, cloud_n, ref_pos, ref_yaw, ellipsoid,
                            bbox3 ? bbox3[0] : 2.0, bbox3 ? bbox3[1] : 2.0, bbox3 ? bbox3[2] : 1.0,
                            poly_A, poly_b, poly_m, poly_idx, n_poly, overflow};
@@ -525,11 +625,9 @@ int nmpc_propagate_ellipsoids_f64(int B, int N, const double* z, const nmpc_elli
     nmpc::EllipsoidParams q{B, N, z, ellipsoid, c.mass, c.drag, c.ego_r, c.ego_h, c.ext_noise_bound, c.epsilon, c.Ts};
     const size_t smem = nmpc::ellipsoid_smem_bytes(N);
     if (smem > 200 * 1024) return fail(NMPC_ERR_ARG, "horizon too long for the ellipsoid kernel: N=%d", N);
-    static thread_local size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        CUDA_TRY(cudaFuncSetAttribute(nmpc::ellipsoid_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (smem > 48 * 1024)
+        if (int rc = ensure_smem(nmpc::ellipsoid_propagate_kernel, smem, configured)) return rc;
     nmpc::ellipsoid_propagate_kernel<<<(B + nmpc::ELL_WARPS - 1) / nmpc::ELL_WARPS, 32 * nmpc::ELL_WARPS, smem,
                                        reinterpret_cast<cudaStream_t>(stream)>>>(q);
     CUDA_TRY(cudaGetLastError());

@@ -36,25 +36,28 @@ namespace nmpc {
 
 struct Opts {
     double mu0, sigma, mu_floor, tol_stat, tol_eq, tol_ineq, tol_comp, kappa_push, s_floor;
-    int maxit, max_bt, pc, reserved;
+    int maxit, max_bt, pc, mixed;
 };
 
+// Problem data and results are arrays of T in HBM, or -- io32, fp64 kernel only: the re-solve of the
+// problems the mixed-precision kernel gave up on (nmpc_ipm_mixed.cuh) -- arrays of float.
 template <typename T> struct Params {
-    int B, mcap, variant;
-    const T* xinit;    // [B][9]
-    const T* z0;       // [B][N][17]
-    const T* hdr;      // [B][N][10]
-    const T* rows;     // [B][N][mcap][4]
+    int B, mcap, variant, io32;
+    const void* xinit;    // [B][9]
+    const void* z0;       // [B][N][17]
+    const void* hdr;      // [B][N][10]
+    const void* rows;     // [B][N][mcap][4]
     const int* nrows;  // [B][N]
     const int* order;  // [B] or nullptr: CTA i solves problem order[i] (launch order = scheduling order)
-    T* z_out;          // [B][N][17]
-    int* info_int;     // [B][4]  exitflag, iterations, backtracks, reserved
-    T* info_real;      // [B][8]  res_eq res_ineq rsnorm rcompnorm pobj mu alpha_p alpha_d
+    const int* count;  // nullptr, or device counter: only the first *count entries of `order` are live
+    void* z_out;          // [B][N][17]
+    int* info_int;     // [B][4]  exitflag, iterations, backtracks, 1 if this is a re-solve (count != nullptr)
+    void* info_real;      // [B][8]  res_eq res_ineq rsnorm rcompnorm pobj mu alpha_p alpha_d
     // optional multiplier outputs (nullptr = not wanted); used by the KKT-acceptance tests
-    T* y_out;          // [B][N][13]  equality multipliers, c-ordering, y[0] = 0
-    T* zl_out;         // [B][N][17]  lower-bound multipliers
-    T* zu_out;         // [B][N][17]  upper-bound multipliers
-    T* lc_out;         // [B][N][mcap] corridor multipliers
+    void* y_out;          // [B][N][13]  equality multipliers, c-ordering, y[0] = 0
+    void* zl_out;         // [B][N][17]  lower-bound multipliers
+    void* zu_out;         // [B][N][17]  upper-bound multipliers
+    void* lc_out;         // [B][N][mcap] corridor multipliers
     Opts o;
 };
 
@@ -260,8 +263,8 @@ template <typename T, int N, bool PC = false> struct Solver {
     T* sm;        // T region
     int* nr;      // live rows per stage
     int lane, mcap, SS;
-    const T* rows_g;   // this problem's corridor rows in global memory, [N][mcap][4] = (a0 a1 a2 b)
-    bool final_variant;
+    const void* rows_g;   // this problem's corridor rows in global memory, [N][mcap][4] = (a0 a1 a2 b)
+    bool final_variant, io32 = false;
     T *Z, *DZ, *ZL, *ZU, *G, *Y, *P, *D, *JC, *PHID, *KG, *KFF, *HDR, *S, *LC, *BND;
     T *QINV, *PQQ0, *DZAP;   // predictor-corrector only
     T* fac_out = nullptr;   // when set, riccati_backward streams the factor ([P: N x 91][K | Quu^-1 | J: N x 113]) to HBM
@@ -304,7 +307,14 @@ template <typename T, int N, bool PC = false> struct Solver {
     // corridor row j of stage k: (a0, a1, a2, b), read-only path (LDG.128, L1-resident across iterations)
     __device__ __forceinline__ void load_row(int k, int j, T (&r)[4]) const
     {
-        const T* p = rows_g + (size_t)(k * mcap + j) * 4;
+        if constexpr (sizeof(T) == 8) {
+            if (io32) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(rows_g) + (size_t)(k * mcap + j) * 4));
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+                return;
+            }
+        }
+        const T* p = static_cast<const T*>(rows_g) + (size_t)(k * mcap + j) * 4;
         if constexpr (sizeof(T) == 8) {
             const double2 a = __ldg(reinterpret_cast<const double2*>(p)), c = __ldg(reinterpret_cast<const double2*>(p) + 1);
             r[0] = a.x; r[1] = a.y; r[2] = c.x; r[3] = c.y;
@@ -1000,8 +1010,11 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= prm.B) return;
+    if (prm.count && (int)blockIdx.x >= *prm.count) return;
     const int b = prm.order ? prm.order[blockIdx.x] : (int)blockIdx.x;
     const int mcap = prm.mcap;
+    const bool io32 = sizeof(T) == 8 && prm.io32 != 0;
+    const size_t esz = io32 ? 4 : sizeof(T);
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* nr = reinterpret_cast<int*>(smem_raw + 16);
@@ -1010,23 +1023,30 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     Solver<T, N, PC> s;
     s.bind(smem_raw, lane, mcap);
     s.final_variant = (prm.variant == 1);
+    s.io32 = io32;
     T* const stg = sm + L::sh_off(mcap);   // TMA staging area = start of SH
     const Opts& o = prm.o;
 
     // ---- stage the problem into shared memory with TMA bulk copies ------------------------
-    const uint32_t bytes_z = N * NZ * sizeof(T), bytes_h = N * 10 * sizeof(T), bytes_n = N * 4;
-    s.rows_g = prm.rows + (size_t)b * N * mcap * 4;
+    const uint32_t bytes_z = (uint32_t)(N * NZ * esz), bytes_h = (uint32_t)(N * 10 * esz), bytes_n = N * 4;
+    s.rows_g = static_cast<const unsigned char*>(prm.rows) + (size_t)b * N * mcap * 4 * esz;
+    T* const stg_z = stg + L::STG_HDR + N * 10;   // io32 only: the float warm start waits here for its conversion
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, bytes_z + bytes_h + bytes_n);
-        tma_load(s.Z, prm.z0 + (size_t)b * N * NZ, bytes_z, bar);
-        tma_load(stg + L::STG_HDR, prm.hdr + (size_t)b * N * 10, bytes_h, bar);
+        tma_load(io32 ? stg_z : s.Z, static_cast<const unsigned char*>(prm.z0) + (size_t)b * N * NZ * esz, bytes_z, bar);
+        tma_load(stg + L::STG_HDR, static_cast<const unsigned char*>(prm.hdr) + (size_t)b * N * 10 * esz, bytes_h, bar);
         tma_load(nr, prm.nrows + (size_t)b * N, bytes_n, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
     // re-layout the headers into a bank-conflict-free padded stride: N*10 -> N*11 (HDR lives beyond the staging alias)
-    for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = stg[L::STG_HDR + e];
+    if (io32) {
+        for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = (T) reinterpret_cast<const float*>(stg + L::STG_HDR)[e];
+        for (int e = lane; e < N * NZ; e += 32) s.Z[e] = (T) reinterpret_cast<const float*>(stg_z)[e];
+    } else {
+        for (int e = lane; e < N * 10; e += 32) s.HDR[(e / 10) * L::HDR_S + (e % 10)] = stg[L::STG_HDR + e];
+    }
     __syncwarp();
 
     // ---- initial point -------------------------------------------------------------------
@@ -1037,7 +1057,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
 #pragma unroll
         for (int i = 0; i < NZ; i++) {
             T v = s.Z[k * NZ + i];
-            if (k == 0 && i >= 8) v = prm.xinit[(size_t)b * 9 + i - 8];
+            if (k == 0 && i >= 8)
+                v = io32 ? (T) static_cast<const float*>(prm.xinit)[(size_t)b * 9 + i - 8] : static_cast<const T*>(prm.xinit)[(size_t)b * 9 + i - 8];
             if (is_free(k, i)) {
                 const T lb = lower_bound<T>(i), ub = upper_bound<T>(i), kp = (T)o.kappa_push;
                 const T pl = fmin(kp * fmax(T(1), fabs(lb)), kp * (ub - lb));
@@ -1157,24 +1178,31 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
 
     // ---- results -----------------------------------------------------------------------------
     __syncwarp();
+    auto put = [&](void* base, size_t idx, T v) {
+        if (io32) static_cast<float*>(base)[idx] = (float)v; else static_cast<T*>(base)[idx] = v;
+    };
+    if (io32) {
+        for (int e = lane; e < N * NZ; e += 32) put(prm.z_out, (size_t)b * N * NZ + e, s.Z[e]);
+    } else if (lane == 0) {
+        tma_store(static_cast<T*>(prm.z_out) + (size_t)b * N * NZ, s.Z, bytes_z);
+    }
     if (lane == 0) {
-        tma_store(prm.z_out + (size_t)b * N * NZ, s.Z, bytes_z);
         int* ii = prm.info_int + (size_t)b * 4;
-        ii[0] = flag; ii[1] = it; ii[2] = nbt_total; ii[3] = 0;
-        T* ir = prm.info_real + (size_t)b * 8;
-        ir[0] = req_n; ir[1] = rin_n; ir[2] = rs_n; ir[3] = rcomp;
-        ir[4] = f_cur; ir[5] = mu; ir[6] = alpha_p; ir[7] = alpha_d;
+        ii[0] = flag; ii[1] = it; ii[2] = nbt_total; ii[3] = prm.count ? 1 : 0;
+        const T v[8] = {req_n, rin_n, rs_n, rcomp, f_cur, mu, alpha_p, alpha_d};
+#pragma unroll
+        for (int q = 0; q < 8; q++) put(prm.info_real, (size_t)b * 8 + q, v[q]);
     }
     if (prm.y_out)
-        for (int e = lane; e < N * NXI; e += 32) prm.y_out[(size_t)b * N * NXI + e] = (e < NXI) ? T(0) : s.Y[e];
+        for (int e = lane; e < N * NXI; e += 32) put(prm.y_out, (size_t)b * N * NXI + e, (e < NXI) ? T(0) : s.Y[e]);
     if (prm.zl_out)
-        for (int e = lane; e < N * NZ; e += 32) prm.zl_out[(size_t)b * N * NZ + e] = s.ZL[e];
+        for (int e = lane; e < N * NZ; e += 32) put(prm.zl_out, (size_t)b * N * NZ + e, s.ZL[e]);
     if (prm.zu_out)
-        for (int e = lane; e < N * NZ; e += 32) prm.zu_out[(size_t)b * N * NZ + e] = s.ZU[e];
+        for (int e = lane; e < N * NZ; e += 32) put(prm.zu_out, (size_t)b * N * NZ + e, s.ZU[e]);
     if (prm.lc_out)
         for (int e = lane; e < N * mcap; e += 32) {
             const int k = e / mcap, j = e - k * mcap;
-            prm.lc_out[(size_t)b * N * mcap + e] = (j < s.live(k)) ? s.LC[k * s.SS + j] : T(0);
+            put(prm.lc_out, (size_t)b * N * mcap + e, (j < s.live(k)) ? s.LC[k * s.SS + j] : T(0));
         }
 }
 

@@ -6,6 +6,9 @@ libnmpc_b200.so.  Three ways in, all ending in the same CUDA kernel:
   * `DeviceBatch` + `solve_device`   inputs resident in HBM (what `bench.py` times as `value`)
   * `solve_host`                     host numpy arrays, H2D + solve + D2H inside the C call
                                      (what `bench.py` times as `e2e`)
+    float32 arrays select the mixed-precision kernel (nmpc_solve_batch_f32: single-precision Newton
+    system, double-precision iterate and residuals, the reference tolerances); `mixed=True` selects it
+    for float64 arrays (nmpc_solve_batch_mixed_f64)
   * `forces.FORCESNormal/FORCESFinal` the reference wrapper classes over the reference ABI
 """
 from __future__ import annotations
@@ -28,6 +31,7 @@ class Result:
     it: np.ndarray         # [B] iterations
     nbt: np.ndarray        # [B] backtracking steps
     info_real: np.ndarray  # [B, 8] res_eq res_ineq rsnorm rcompnorm pobj mu alpha_p alpha_d
+    resolved: np.ndarray | None = None   # [B] 1 where the mixed-precision kernel handed the problem to the fp64 kernel
 
 
 def _check(rc: int):
@@ -39,11 +43,14 @@ def _np_ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_host(batch: Batch, dtype=np.float64, opts: _lib.NmpcOpts | None = None) -> Result:
-    """Host buffers in, host buffers out: nmpc_solve_batch_host_{f64,f32}."""
+def solve_host(batch: Batch, dtype=np.float64, opts: _lib.NmpcOpts | None = None, mixed: bool = False) -> Result:
+    """Host buffers in, host buffers out: nmpc_solve_batch_host_{f64,f32,mixed_f64}."""
     lib = _lib.load()
     dtype = np.dtype(dtype)
-    fn = lib.nmpc_solve_batch_host_f64 if dtype == np.float64 else lib.nmpc_solve_batch_host_f32
+    if dtype == np.float64:
+        fn = lib.nmpc_solve_batch_host_mixed_f64 if mixed else lib.nmpc_solve_batch_host_f64
+    else:
+        fn = lib.nmpc_solve_batch_host_f32
     B, N, mcap = batch.B, batch.N, batch.mcap
     xinit = np.ascontiguousarray(batch.xinit, dtype)
     z0 = np.ascontiguousarray(batch.z0, dtype)
@@ -56,7 +63,7 @@ def solve_host(batch: Batch, dtype=np.float64, opts: _lib.NmpcOpts | None = None
     o = opts or _lib.default_opts()
     _check(fn(B, N, mcap, _np_ptr(xinit), _np_ptr(z0), _np_ptr(hdr), _np_ptr(rows), _np_ptr(nrows),
               int(batch.variant), ctypes.byref(o), _np_ptr(z), _np_ptr(ii), _np_ptr(ir)))
-    return Result(z, ii[:, 0].copy(), ii[:, 1].copy(), ii[:, 2].copy(), ir)
+    return Result(z, ii[:, 0].copy(), ii[:, 1].copy(), ii[:, 2].copy(), ir, ii[:, 3].copy())
 
 
 class DeviceBatch:
@@ -97,33 +104,39 @@ class DeviceBatch:
         self.torch.cuda.synchronize(self.device)
         ii = self.info_int.cpu().numpy()
         return Result(self.z.cpu().numpy(), ii[:, 0].copy(), ii[:, 1].copy(), ii[:, 2].copy(),
-                      self.info_real.cpu().numpy())
+                      self.info_real.cpu().numpy(), ii[:, 3].copy())
 
 
-def solve_device(db: DeviceBatch, opts: _lib.NmpcOpts | None = None, stream=None) -> None:
-    """Enqueue one fused-IPM launch on `stream` (default: torch's current stream)."""
+def solve_device(db: DeviceBatch, opts: _lib.NmpcOpts | None = None, stream=None, mixed: bool = False) -> None:
+    """Enqueue one solve on `stream` (default: torch's current stream): the fp64 kernel for float64 batches, the
+    mixed-precision kernel (+ its fp64 re-solve of the few problems it gives up on) for float32 batches or `mixed`."""
     lib = _lib.load()
     torch = db.torch
-    fn = lib.nmpc_solve_batch_f64 if db.np_dtype == np.float64 else lib.nmpc_solve_batch_f32
     st = stream if stream is not None else torch.cuda.current_stream(db.device)
     o = opts or _lib.default_opts()
     d = db.d
+    args = [db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
+            d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
+            db.z.data_ptr(), db.info_int.data_ptr(), db.info_real.data_ptr()]
     with torch.cuda.device(db.device):
-        _check(fn(db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
-                  d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
-                  db.z.data_ptr(), db.info_int.data_ptr(), db.info_real.data_ptr(),
-                  ctypes.c_void_p(st.cuda_stream)))
+        if db.np_dtype == np.float32:
+            _check(lib.nmpc_solve_batch_f32(*args, ctypes.c_void_p(st.cuda_stream)))
+        elif mixed:
+            _check(lib.nmpc_solve_batch_mixed_f64(*args, None, None, None, None, None, ctypes.c_void_p(st.cuda_stream)))
+        else:
+            _check(lib.nmpc_solve_batch_f64(*args, ctypes.c_void_p(st.cuda_stream)))
 
 
-def solve(batch: Batch, dtype=np.float64, opts=None, device="cuda:0") -> Result:
+def solve(batch: Batch, dtype=np.float64, opts=None, device="cuda:0", mixed: bool = False) -> Result:
     """Convenience: upload, solve on the device, download."""
     db = DeviceBatch(batch, dtype, device)
-    solve_device(db, opts)
+    solve_device(db, opts, mixed=mixed)
     return db.result()
 
 
-def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0"):
-    """fp64 solve that also returns the multipliers of the KKT point (nmpc_solve_batch_ex_f64).
+def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0", mixed: bool = False):
+    """fp64-array solve that also returns the multipliers of the KKT point (nmpc_solve_batch_ex_f64, or
+    nmpc_solve_batch_mixed_f64 with `mixed`).
 
     Returns (Result, dict(y, zl, zu, lc)) -- what the KKT-acceptance tests need to re-evaluate
     ForcesPro's stopping test with the reference callbacks."""
@@ -135,17 +148,16 @@ def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0"):
     lc = mk(db.B, db.N, max(db.mcap, 1))
     o = opts or _lib.default_opts()
     d = db.d
-    lib.nmpc_solve_batch_ex_f64.restype = ctypes.c_int
-    lib.nmpc_solve_batch_ex_f64.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int] + \
-        [ctypes.POINTER(_lib.NmpcOpts)] + [ctypes.c_void_p] * 8
     with torch.cuda.device(db.device):
         st = torch.cuda.current_stream(db.device)
-        _check(lib.nmpc_solve_batch_ex_f64(
-            db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
-            d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
-            db.z.data_ptr(), db.info_int.data_ptr(), db.info_real.data_ptr(),
-            y.data_ptr(), zl.data_ptr(), zu.data_ptr(), lc.data_ptr() if db.mcap else None,
-            ctypes.c_void_p(st.cuda_stream)))
+        args = [db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
+                d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
+                db.z.data_ptr(), db.info_int.data_ptr(), db.info_real.data_ptr(),
+                y.data_ptr(), zl.data_ptr(), zu.data_ptr(), lc.data_ptr() if db.mcap else None]
+        if mixed:
+            _check(lib.nmpc_solve_batch_mixed_f64(*args, None, ctypes.c_void_p(st.cuda_stream)))
+        else:
+            _check(lib.nmpc_solve_batch_ex_f64(*args, ctypes.c_void_p(st.cuda_stream)))
     res = db.result()
     return res, dict(y=y.cpu().numpy(), zl=zl.cpu().numpy(), zu=zu.cpu().numpy(),
                      lc=lc.cpu().numpy()[:, :, :db.mcap])

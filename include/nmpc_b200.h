@@ -56,24 +56,20 @@ typedef struct nmpc_opts {
     int max_bt;        /* backtracking steps per iteration                   (default 6)     */
     int pc;            /* 1: Mehrotra predictor-corrector -- affine solve, sigma = (mu_aff/mu)^3, second-order
                           corrector through the same factorisation (default 0; fp64 entry points only)   */
-    int reserved;
+    int mixed;         /* *_f32 / *_mixed_* entry points: -1 disables the fp64 re-solve of the problems the mixed-precision
+                          kernel does not bring to exit flag 1 (default 0 = re-solve them).  Ignored by the fp64 entry
+                          points.  (The CPU oracle shares this struct; there 1 selects its mixed-precision restatement.) */
 } nmpc_opts;
 
 void nmpc_default_opts(nmpc_opts *o);
-/* options for the *_f32 entry points: the reference tolerances (absolute 1e-4 on gradients of order
- * 1e2..1e3) are below single-precision resolution; these are the tightest values at which every
- * BASELINE config-3 problem converges in fp32: tol_stat 2e-2, tol_comp 1e-2, mu_floor 1e-3,
- * tol_eq / tol_ineq unchanged (1e-4).  Solutions then agree with the fp64 KKT point to ~6e-2
- * (max) / 3e-3 (median) in z; use the fp64 entry points whenever the reference tolerances matter. */
-void nmpc_default_opts_f32(nmpc_opts *o);
 const char *nmpc_last_error(void);
 const char *nmpc_version(void);
 
 /* Supported horizons N: 20 (the reference), 40 (BASELINE config 4).  mcap in [0, 32]. */
 int nmpc_supported_horizon(int N);
-/* dynamic shared memory one problem occupies (bytes); elem_size 8 (f64) or 4 (f32) */
+/* dynamic shared memory one problem occupies (bytes): elem_size 8 = the fp64 kernel, 4 = the mixed-precision kernel */
 long nmpc_smem_bytes(int N, int mcap, int elem_size);
-long nmpc_smem_bytes_pc(int N, int mcap, int elem_size);   /* the same for the predictor-corrector kernel (opts.pc = 1) */
+long nmpc_smem_bytes_pc(int N, int mcap, int elem_size);   /* the fp64 predictor-corrector kernel (opts.pc = 1); elem_size 8 only */
 
 /* ---- device-pointer API: everything already resident in HBM, asynchronous on `stream` --------
  * z0, hdr, rows, nrows and z_out must be 16-byte aligned (TMA bulk copies / 16-byte vector loads);
@@ -82,10 +78,29 @@ int nmpc_solve_batch_f64(int B, int N, int mcap, const double *xinit, const doub
                          const double *hdr, const double *rows, const int *nrows, int variant,
                          const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,
                          void *cuda_stream);
+
+/* ---- mixed precision (BASELINE configs 3 and 4, "fp32") -------------------------------------------
+ * Same problem, same REFERENCE tolerances (nmpc_default_opts: 1e-4 inf-norms, mpc_generator_normal.m:76-79), same
+ * exit codes.  The Newton system (stage Hessians, Jacobians, right-hand side, Riccati recursion, rollout, costates)
+ * is formed and solved in single precision in DELTA form; the iterate, the model evaluation, the KKT residuals
+ * that decide termination, the step rule and the line search are double precision, so the outer iteration refines
+ * the single-precision solve (csrc/nmpc_ipm_mixed.cuh).  Problems the single-precision factorisation cannot carry
+ * (non-positive pivot on badly scaled instances, exit -5; or no convergence within 60 iterations) are re-solved by
+ * the fp64 kernel on the same stream before the call's work completes; they carry info_int[b][3] = 1.
+ *   nmpc_solve_batch_f32        problem data and results are float arrays in HBM
+ *   nmpc_solve_batch_mixed_f64  problem data and results are double arrays; optionally the multipliers (as
+ *                               nmpc_solve_batch_ex_f64; any may be NULL) and a scheduling order (as
+ *                               nmpc_solve_batch_ordered_f64; NULL = natural order)
+ * opts->pc is ignored (no predictor-corrector variant).                                                  */
 int nmpc_solve_batch_f32(int B, int N, int mcap, const float *xinit, const float *z0,
                          const float *hdr, const float *rows, const int *nrows, int variant,
                          const nmpc_opts *opts, float *z_out, int *info_int, float *info_real,
                          void *cuda_stream);
+int nmpc_solve_batch_mixed_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                               const double *hdr, const double *rows, const int *nrows, int variant,
+                               const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,
+                               double *y_out, double *zl_out, double *zu_out, double *lc_out,
+                               const int *order, void *cuda_stream);
 
 /* as nmpc_solve_batch_f64, additionally returning the multipliers of the KKT point (any of the
  * four may be NULL): y_out [B][N][13] (c-ordering [x+(9); u(4)], y[0] = 0), zl_out / zu_out
@@ -110,9 +125,13 @@ int nmpc_solve_batch_ordered_f64(int B, int N, int mcap, const double *xinit, co
 int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double *xinit, const double *z0,
                               const double *hdr, const double *rows, const int *nrows, int variant,
                               const nmpc_opts *opts, double *z_out, int *info_int, double *info_real);
+/* host-pointer forms of the mixed-precision solve (float arrays / double arrays) */
 int nmpc_solve_batch_host_f32(int B, int N, int mcap, const float *xinit, const float *z0,
                               const float *hdr, const float *rows, const int *nrows, int variant,
                               const nmpc_opts *opts, float *z_out, int *info_int, float *info_real);
+int nmpc_solve_batch_host_mixed_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                                    const double *hdr, const double *rows, const int *nrows, int variant,
+                                    const nmpc_opts *opts, double *z_out, int *info_int, double *info_real);
 
 /* ---- stand-alone structured KKT factorisation / backsolve (device pointers) ------------------
  * The split the reference binary makes internally (f_17_PD_ldlchol_rowmajor ... vs

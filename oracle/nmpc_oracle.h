@@ -42,7 +42,8 @@ typedef struct {
     int maxit;         /* iteration cap (codeoptions.maxit 200)                       */
     int max_bt;        /* backtracking steps per iteration                            */
     int pc;            /* 1: Mehrotra predictor-corrector (affine solve -> sigma, corrector rhs)  */
-    int reserved;
+    int mixed;         /* 1: delta-form Newton system solved by a SINGLE-precision Riccati recursion, everything
+                          else (iterate, residuals, step rule, line search) in `real`; see nmpc_oracle.c  */
 } nmpc_oracle_opts;
 
 void nmpc_oracle_default_opts(nmpc_oracle_opts *o);

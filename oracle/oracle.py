@@ -19,7 +19,7 @@ class OracleOpts(ctypes.Structure):
                 ("tol_stat", ctypes.c_double), ("tol_eq", ctypes.c_double),
                 ("tol_ineq", ctypes.c_double), ("tol_comp", ctypes.c_double),
                 ("kappa_push", ctypes.c_double), ("s_floor", ctypes.c_double),
-                ("maxit", ctypes.c_int), ("max_bt", ctypes.c_int), ("pc", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("maxit", ctypes.c_int), ("max_bt", ctypes.c_int), ("pc", ctypes.c_int), ("mixed", ctypes.c_int)]
 
 
 def build(force: bool = False) -> None:

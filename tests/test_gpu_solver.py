@@ -225,23 +225,64 @@ def test_cpp_dropin_demo_runs_the_planner_call_sequence():
     assert out.stdout.count("64/64 accepted") == 3 and out.stdout.count("corridor overflow 0") == 3, out.stdout
 
 
-def test_fp32_entry_point_at_its_stated_tolerance():
-    """BASELINE configs 3/4 name fp32.  Single precision cannot resolve the reference's absolute 1e-4
-    tolerances on this problem, so the *_f32 entry points come with their own
-    stated options (nmpc_default_opts_f32) and tolerance: every problem converges, equalities and
-    corridor rows still hold to 1e-3 when re-evaluated in fp64, and the point is within 6e-2 (max) /
-    5e-3 (median) of the fp64 KKT point."""
-    for b in (W.config3(1024), W.config4(16, 40)):
-        g = S.solve_host(b, np.float32, opts=_lib.default_opts(f32=True))
-        c = O.solve_batch(b)
-        assert np.all(g.flag == 1) and np.all(c["flag"] == 1)
-        dz = np.abs(g.z.astype(np.float64) - c["z"]).reshape(b.B, -1).max(1)
-        assert dz.max() < 6e-2 and np.median(dz) < 5e-3
-        z = g.z.astype(np.float64)
-        assert np.max(np.abs(z[:, 1:, 4:8] - z[:, :-1, 0:4])) < 1e-3          # u_prev chain
-        viol = np.einsum("bkmj,bkj->bkm", b.rows[:, 1:, :, 0:3], z[:, 1:, 8:11]) - b.rows[:, 1:, :, 3] - 1e-5
-        live = np.arange(b.mcap)[None, None, :] < b.nrows[:, 1:, None]
-        assert np.where(live, viol, -1.0).max() < 1e-3
+MIXED_CASES = [(W.config2, dict(B=512)), (W.config3, dict(B=1024)), (W.config2, dict(B=128, variant=1)),
+               (W.config4, dict(side=16, n_stages=40))]
+
+
+@pytest.mark.parametrize("maker,kw", MIXED_CASES)
+def test_mixed_precision_meets_the_reference_tolerances(maker, kw):
+    """BASELINE configs 3/4 name fp32.  The *_f32 entry points run the mixed-precision kernel (single-precision
+    Newton system in delta form, double-precision iterate / residuals / line search) with nmpc_default_opts
+    UNCHANGED: the reference's 1e-4 stopping test (mpc_generator_normal.m:76-79).  Stated tolerance: every problem
+    ends with exit flag 1, |z - z_fp64_oracle|_inf <= 1e-3 (SURVEY.md 8c pin 4; measured ~5e-4 worst, 1e-6 median --
+    both solvers stop anywhere inside the 1e-4 residual ball), iteration counts as the fp64 solver's."""
+    b = maker(**kw)
+    c = O.solve_batch(b)
+    assert np.all(c["flag"] == 1)
+    for res in (S.solve_host(b, np.float32), S.solve_host(b, np.float64, mixed=True)):
+        assert np.all(res.flag == 1), np.unique(res.flag, return_counts=True)
+        assert np.all(res.info_real[:, 0:4] <= TOL * (1 + 1e-6))
+        dz = np.abs(res.z.astype(np.float64) - c["z"]).reshape(b.B, -1).max(1)
+        assert dz.max() < 1e-3 and np.median(dz) < 2e-5, (dz.max(), np.median(dz))
+        assert abs(res.it.mean() - c["it"].mean()) < 0.05 * c["it"].mean()
+        assert res.resolved.mean() <= 0.05          # the fp64 safety net is the exception, not the path
+    # the CPU restatement of the same algorithm (oracle opts.mixed = 1: dense single-precision Riccati) walks the same path
+    m = O.solve_batch(b, opts=O.default_opts(mixed=1))
+    same = (m["flag"] == 1) & (res.resolved == 0)
+    assert np.mean(np.abs(res.it[same] - m["it"][same]) <= 1) >= 0.97
+
+
+def test_mixed_precision_kkt_points_pass_forcespro_acceptance_with_reference_callbacks():
+    for b in (W.config3(96), W.config2(48, variant=1)):
+        res, mult = S.solve_with_multipliers(b, mixed=True)
+        assert np.all(res.flag == 1)
+        model = _model(b.variant)
+        for i in range(0, b.B, 4):
+            r = H.kkt_residuals(b, i, res.z[i], mult["y"][i], mult["zl"][i], mult["zu"][i], mult["lc"][i], model)
+            assert max(r) <= TOL, (i, r)
+            assert abs(r[0] - res.info_real[i, 2]) < 1e-6      # the fp64 residual the kernel stops on is honest
+            assert min(mult["zl"][i].min(), mult["zu"][i].min(), mult["lc"][i].min()) >= 0.0
+
+
+def test_mixed_precision_hands_unsolved_problems_to_the_fp64_kernel():
+    """The safety net, made deterministic: with an iteration cap of 3 the mixed kernel leaves every problem at exit
+    flag 0, so ALL of them are re-solved by the fp64 kernel (from the float / double arrays of the caller, on the
+    same stream) -- the results must be exactly the fp64 kernel's own with that cap, and carry the re-solve mark.
+    opts.mixed = -1 switches the net off."""
+    b = W.config3(300)
+    o = _lib.default_opts(maxit=3)
+    ref = S.solve_host(b, np.float64, opts=o)
+    assert np.all(ref.flag == 0) and np.all(ref.it == 3)
+    m = S.solve_host(b, np.float64, opts=o, mixed=True)
+    assert np.all(m.resolved == 1) and np.array_equal(m.z, ref.z) and np.array_equal(m.flag, ref.flag)
+    # float arrays: the fp64 kernel reads and writes them directly (io32)
+    b32 = b.astype(np.float32).astype(np.float64)
+    ref32 = S.solve_host(b32, np.float64, opts=o)
+    m32 = S.solve_host(b, np.float32, opts=o)
+    assert np.all(m32.resolved == 1) and np.array_equal(m32.z, ref32.z.astype(np.float32))
+    off = S.solve_host(b, np.float64, opts=_lib.default_opts(maxit=3, mixed=-1), mixed=True)
+    assert np.all(off.resolved == 0) and np.all(off.flag == 0)
+    assert np.max(np.abs(off.z - ref.z)) < 1e-3         # three iterations of the same algorithm in mixed precision
 
 
 def test_receding_horizon_stream_matches_cpu_closed_loop():
