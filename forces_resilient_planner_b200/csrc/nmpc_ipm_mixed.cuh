@@ -12,9 +12,12 @@
 //                     recursion (cost-to-go, gains), the forward rollout and the costate sweep.
 //
 // The Newton system is written in DELTA form: its right-hand side is the full KKT residual at the current
-// (z, y) -- gradient of the Lagrangian W = grad f + J'y - E'y, evaluated in double precision while the
-// Jacobian of the accepted trial point is still in registers -- so the unknowns are (dz, dy) and the rounding
-// of the single-precision solve is relative to the STEP, not to the multipliers.  The outer Newton iteration
+// point -- the stationarity residual r = grad f + J'y - E'y - z_l + z_u + A'lambda is evaluated in double
+// precision while the Jacobian of the accepted trial point is still in registers, its inf-norm taken there, and
+// only then is it rounded (a residual may be rounded: the error is relative to r itself) -- so the unknowns are
+// (dz, dy) and the rounding of the single-precision solve is relative to the STEP, not to the multipliers.
+// For r to be available at the trial point the multiplier steps (which do not depend on the primal step
+// length) are taken BEFORE the line search; nothing else of the algorithm changes.  The outer Newton iteration
 // thereby acts as iterative refinement; on BASELINE configs 2 / 3 the iteration counts equal the fp64
 // solver's (oracle restatement: oracle/nmpc_oracle.c, opts.mixed = 1).
 //
@@ -23,7 +26,7 @@
 // cancellation in P = Q_xx - Y'Y).  Those warps stop with the reference's factorisation code (-5) and the
 // host entry point re-solves exactly those problems with the fp64 kernel (nmpc_capi.cu: solve_mixed).
 //
-// Shared memory per problem (N = 20, 8 rows): 17.9 KB of fp64 state + 10.6 KB of fp32 Newton data; the
+// Shared memory per problem (N = 20, 8 rows): 15.2 KB of fp64 state + 10.6 KB of fp32 Newton data; the
 // fp32 sweep-private arrays (gains, Riccati scratch: 7.8 KB) are overlaid on the fp64 state, which is parked
 // in 31 registers per lane across the sweeps -- the same trick as the fp64 kernel at half its register cost.
 #pragma once
@@ -60,8 +63,7 @@ template <int N> struct MLayout {
     static constexpr int Y = ZU + N * NZ;
     static constexpr int HDR = Y + N * NXI;
     static constexpr int BND = HDR + N * HDR_S;
-    static constexpr int W = BND + 2 * NZ;          // gradient of the Lagrangian at the accepted trial point
-    static constexpr int R_FIXED = W + N * NZ;
+    static constexpr int R_FIXED = BND + 2 * NZ;
     __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
     __host__ __device__ static constexpr int s_off(int) { return R_FIXED; }
     __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
@@ -78,7 +80,7 @@ template <int N> struct MLayout {
         return ((r_end(mcap) > NPARK ? r_end(mcap) : NPARK) + 1) & ~1;
     }
     static constexpr int SH_DZ = 0;
-    static constexpr int SH_G = SH_DZ + N * NZ;
+    static constexpr int SH_G = SH_DZ + N * NZ;      // stationarity residual of the trial point, then the right-hand side
     static constexpr int SH_DY = SH_G + N * NZ;      // p_k during the backward sweep, then dy (costates of the QP)
     static constexpr int SH_D = SH_DY + N * NXI;
     static constexpr int SH_JC = SH_D + N * NXI;
@@ -103,7 +105,7 @@ template <int N> struct MixedSolver {
     int lane, mcap, SS;
     const void* rows_g;
     bool io32, final_variant;
-    double *Z, *ZL, *ZU, *Y, *HDR, *BND, *W, *S, *LC;
+    double *Z, *ZL, *ZU, *Y, *HDR, *BND, *S, *LC;
     float *DZ, *G, *DY, *D, *JC, *PHID;
     Solver<float, N, false> sw;   // the single-precision sweeps, bound to the overlay + SH
 
@@ -113,7 +115,7 @@ template <int N> struct MixedSolver {
         nr = reinterpret_cast<int*>(smem_raw + 16);
         lane = lane_; mcap = mcap_; SS = ML::s_stride(mcap);
         Z = r64 + ML::Z; ZL = r64 + ML::ZL; ZU = r64 + ML::ZU; Y = r64 + ML::Y; HDR = r64 + ML::HDR; BND = r64 + ML::BND;
-        W = r64 + ML::W; S = r64 + ML::s_off(mcap); LC = r64 + ML::lc_off(mcap);
+        S = r64 + ML::s_off(mcap); LC = r64 + ML::lc_off(mcap);
         float* sh = reinterpret_cast<float*>(r64 + ML::sh_off_d(mcap));
         DZ = sh + ML::SH_DZ; G = sh + ML::SH_G; DY = sh + ML::SH_DY; D = sh + ML::SH_D; JC = sh + ML::SH_JC; PHID = sh + ML::SH_PHID;
         float* ovl = reinterpret_cast<float*>(r64);
@@ -153,12 +155,13 @@ template <int N> struct MixedSolver {
     }
 
     // ---------------------------------------------------------------- model evaluation ---
-    // At (z + a dz, y + a dy), all in double precision ("lanes = stages"): cost, defects, theta, barrier
-    // log-sum, and the gradient of the Lagrangian W = grad f + J'y+ - E'y+ formed while the Jacobian is in
-    // registers.  What the single-precision Newton solve needs (compact Jacobian, defects) is rounded on the way out.
-    __device__ void evaluate(double a, double& f_out, double& th_out, double& ls_out, double& req_out)
+    // At (z + a dz, y + a dy) with the multipliers already stepped, all in double precision ("lanes = stages"):
+    // cost, defects, theta, barrier log-sum, and the stationarity residual formed while the Jacobian is in
+    // registers.  What the single-precision Newton solve needs (compact Jacobian, defects, residual) is rounded on
+    // the way out; the norms that decide termination are taken before the rounding.
+    __device__ void evaluate(double a, double& f_out, double& th_out, double& ls_out, double& req_out, double& rs_out)
     {
-        double f = 0.0, th = 0.0, ls = 0.0, rq = 0.0;
+        double f = 0.0, th = 0.0, ls = 0.0, rq = 0.0, rs = 0.0;
         for (int k = lane; k < N; k += 32) {
             double zk[NZ], g[NZ];
 #pragma unroll
@@ -186,8 +189,6 @@ template <int N> struct MixedSolver {
 #pragma unroll
                 for (int i = 0; i < NXI; i++) g[i < 9 ? 8 + i : i - 5] -= Y[k * NXI + i] + a * (double)DY[k * NXI + i];
             }
-#pragma unroll
-            for (int i = 0; i < NZ; i++) W[k * NZ + i] = g[i];
             double prod = 1.0;
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
@@ -197,9 +198,12 @@ template <int N> struct MixedSolver {
                 if (i % 4 == 3 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
             }
             const int m = live(k);
+            double al0 = 0.0, al1 = 0.0, al2 = 0.0;
             for (int j = 0; j < m; j++) {
                 double r[4]; load_row(k, j, r);
                 double sj = S[k * SS + j];
+                const double lj = LC[k * SS + j];
+                al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
                 double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const double adz = r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10];
                 sj += a * (-rc - adz);
@@ -209,58 +213,59 @@ template <int N> struct MixedSolver {
                 if ((j & 7) == 7) { ls += log(prod); prod = 1.0; }
             }
             ls += log(prod);
+            g[8] += al0; g[9] += al1; g[10] += al2;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                double r = g[i] - ZL[k * NZ + i] + ZU[k * NZ + i];
+                if (i >= 8 && k == 0) r = 0.0;                    // stage-0 states are fixed by the xinit equality
+                rs = fmax(rs, fabs(r));
+                G[k * NZ + i] = (float)r;
+            }
         }
-        f_out = warp_sum(f); th_out = warp_sum(th); ls_out = warp_sum(ls); req_out = warp_max(rq);
+        f_out = warp_sum(f); th_out = warp_sum(th); ls_out = warp_sum(ls); req_out = warp_max(rq); rs_out = warp_max(rs);
     }
 
-    // ------------------------------------------------------- residual norms and mu ------
-    __device__ void residuals(double& rs_n, double& rin_n, double& rcomp, double& csum, double& cmin)
+    // ---------------------------------------- inequality residual, complementarity, mu ------
+    __device__ void residuals(double& rin_n, double& rcomp, double& csum, double& cmin)
     {
-        double rs = 0.0, rin = 0.0, cmx = 0.0, cs = 0.0, cmn = 1e30;
+        double rin = 0.0, cmx = 0.0, cs = 0.0, cmn = 1e30;
         for (int k = lane; k < N; k += 32) {
             const int m = live(k);
-            double al0 = 0.0, al1 = 0.0, al2 = 0.0;
             for (int j = 0; j < m; j++) {
                 double r[4]; load_row(k, j, r);
                 const double sj = S[k * SS + j], lj = LC[k * SS + j];
-                al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
                 const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const double cc = sj * lj;
                 cs += cc; cmx = fmax(cmx, cc); cmn = fmin(cmn, cc);
                 rin = fmax(rin, fmax(fabs(rc), rc - sj));
             }
-            const int nfree = (k == 0) ? 8 : NZ;
-#pragma unroll 1
-            for (int i = 0; i < nfree; i++) {
-                const double zi = Z[k * NZ + i], zl = ZL[k * NZ + i], zu = ZU[k * NZ + i];
-                double r = W[k * NZ + i] - zl + zu;
-                if (i >= 8 && i < 11) r += (i == 8 ? al0 : (i == 9 ? al1 : al2));
-                rs = fmax(rs, fabs(r));
-                const double cl = (zi - BND[i]) * zl, cu = (BND[NZ + i] - zi) * zu;
-                cs += cl + cu;
-                cmx = fmax(cmx, fmax(cl, cu));
-                cmn = fmin(cmn, fmin(cl, cu));
-            }
         }
-        rs_n = warp_max(rs); rin_n = warp_max(rin); rcomp = warp_max(cmx);
+        for (int e = lane; e < N * NZ; e += 32) {
+            if (!(e < 8 || e >= NZ)) continue;
+            const int i = e % NZ;
+            const double zi = Z[e];
+            const double cl = (zi - BND[i]) * ZL[e], cu = (BND[NZ + i] - zi) * ZU[e];
+            cs += cl + cu;
+            cmx = fmax(cmx, fmax(cl, cu));
+            cmn = fmin(cmn, fmin(cl, cu));
+        }
+        rin_n = warp_max(rin); rcomp = warp_max(cmx);
         csum = warp_sum(cs); cmin = warp_min(cmn);
     }
 
     // ------------------------- barrier-augmented stage Hessian and right-hand side (-> fp32) ---
-    // The right-hand side W + mu (1/s_u - 1/s_l) + A'((mu + lambda r_c)/s) cancels to ~0 at a KKT point; the
-    // cancellation happens in double precision, only the result is rounded.  W is dead after this phase (the
-    // next evaluation rewrites it), so the position entries are completed in place.
+    // rhs = r + (z_l - mu/s_l) - (z_u - mu/s_u) + A'((mu + lambda r_c)/s - lambda): the stationarity residual r is
+    // in G (single precision), the complementarity terms are formed in double precision from the iterate.
     __device__ void assemble(double mu_t)
     {
         for (int e = lane; e < N * NZ; e += 32) {
             const int k = e / NZ, i = e - k * NZ;
             float* phi = PHID + k * ML::PHI_S;
             if (e < 8 || e >= NZ) {
-                const double zi = Z[e];
+                const double zi = Z[e], zl = ZL[e], zu = ZU[e];
                 const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
-                phi[i] = (float)(cost_hess_diag<double>(i, HDR + k * ML::HDR_S, k == 0, final_variant && k == N - 1) + ZL[e] * isl + ZU[e] * isu);
-                const double gi = W[e] + mu_t * (isu - isl);
-                if (i >= 8 && i < 11) W[e] = gi; else G[e] = (float)gi;
+                phi[i] = (float)(cost_hess_diag<double>(i, HDR + k * ML::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu);
+                G[e] = (float)((double)G[e] + ((zl - mu_t * isl) - (zu - mu_t * isu)));
             } else {
                 phi[i] = 1.0f;
                 G[e] = 0.0f;
@@ -275,7 +280,7 @@ template <int N> struct MixedSolver {
                 double r[4]; load_row(k, j, r);
                 const double sj = S[k * SS + j], lj = LC[k * SS + j], is = 1.0 / sj;
                 const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                const double sg = lj * is, tt = (mu_t + lj * rc) * is;
+                const double sg = lj * is, tt = (mu_t + lj * (rc - sj)) * is;
                 d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
                 o01 += r[0] * r[1] * sg; o02 += r[0] * r[2] * sg; o12 += r[1] * r[2] * sg;
                 g0 += r[0] * tt; g1 += r[1] * tt; g2 += r[2] * tt;
@@ -284,9 +289,9 @@ template <int N> struct MixedSolver {
             phi[17] = (float)o01; phi[18] = (float)o02; phi[19] = (float)o12;
             phi[20] = (float)(-2.0 * HDR[k * ML::HDR_S + 8]);
             if (k > 0) {
-                G[k * NZ + 8] = (float)(W[k * NZ + 8] + g0);
-                G[k * NZ + 9] = (float)(W[k * NZ + 9] + g1);
-                G[k * NZ + 10] = (float)(W[k * NZ + 10] + g2);
+                G[k * NZ + 8] = (float)((double)G[k * NZ + 8] + g0);
+                G[k * NZ + 9] = (float)((double)G[k * NZ + 9] + g1);
+                G[k * NZ + 10] = (float)((double)G[k * NZ + 10] + g2);
             }
         }
     }
@@ -327,8 +332,8 @@ template <int N> struct MixedSolver {
         ad_out = (dn > 0.0) ? fmin(1.0, tau * dd / dn) : 1.0;
     }
 
-    // --------------------------------------------------------------- accept the step ----
-    __device__ void update(double mu_t, double a, double ad)
+    // ---------------------------------------------- multiplier steps (before the line search) ----
+    __device__ void update_duals(double mu_t, double ad)
     {
         for (int k = lane; k < N; k += 32) {
             const int m = live(k);
@@ -337,23 +342,34 @@ template <int N> struct MixedSolver {
                 const double sj = S[k * SS + j], lj = LC[k * SS + j];
                 const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const double ds = -rc - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
-                const double dl = (mu_t - lj * ds) / sj - lj;
+                LC[k * SS + j] = lj + ad * ((mu_t - lj * ds) / sj - lj);
+            }
+        }
+        for (int e = lane; e < N * NZ; e += 32) {
+            if (!(e < 8 || e >= NZ)) continue;
+            const int i = e % NZ;
+            const double zi = Z[e], dzi = (double)DZ[e], zl = ZL[e], zu = ZU[e];
+            const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
+            ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
+            ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
+        }
+    }
+
+    // ------------------------------------------------------- accept the primal step ----
+    __device__ void update_primal(double a)
+    {
+        for (int k = lane; k < N; k += 32) {               // corridor slacks first: they read the old position
+            const int m = live(k);
+            for (int j = 0; j < m; j++) {
+                double r[4]; load_row(k, j, r);
+                const double sj = S[k * SS + j];
+                const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const double ds = -rc - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
                 S[k * SS + j] = sj + a * ds;
-                LC[k * SS + j] = lj + ad * dl;
             }
         }
         __syncwarp();
-        for (int e = lane; e < N * NZ; e += 32) {
-            const double zi = Z[e], dzi = (double)DZ[e];
-            if (e < 8 || e >= NZ) {
-                const int i = e % NZ;
-                const double zl = ZL[e], zu = ZU[e];
-                const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
-                ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
-                ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
-            }
-            Z[e] = zi + a * dzi;
-        }
+        for (int e = lane; e < N * NZ; e += 32) Z[e] += a * (double)DZ[e];
         for (int e = NXI + lane; e < N * NXI; e += 32) Y[e] += a * (double)DY[e];
     }
 };
@@ -446,12 +462,12 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
     int flag = 0, it = 0, nbt_total = 0;
     double alpha_p = 0.0, alpha_d = 0.0, rs_n = 0.0, req_n = 0.0, rin_n = 0.0, rcomp = 0.0, mu = 0.0;
     double f_cur, th_cur, ls_cur;
-    s.evaluate(0.0, f_cur, th_cur, ls_cur, req_n);
+    s.evaluate(0.0, f_cur, th_cur, ls_cur, req_n, rs_n);
     __syncwarp();
     const int it_cap = min(o.maxit, MIXED_BAIL_IT);
     for (it = 0;; it++) {
         double csum, cmin;
-        s.residuals(rs_n, rin_n, rcomp, csum, cmin);
+        s.residuals(rin_n, rcomp, csum, cmin);
         mu = csum / (double)ncomp;
         const bool finite = isfinite(rs_n) && isfinite(req_n) && isfinite(mu) && isfinite(f_cur) && isfinite(th_cur);
         if (!finite) { flag = (it == 0) ? -6 : -7; break; }
@@ -482,13 +498,15 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
         const double tau = fmin(fmax(0.995, 1.0 - mu), 0.99999);
         double ap, ad;
         s.step_lengths(mu_t, tau, ap, ad);
+        s.update_duals(mu_t, ad);       // independent of the primal step length; the trial evaluations see the new multipliers
+        __syncwarp();
         const double ph0 = f_cur - mu_t * ls_cur;
         const double th_noise = fmax(10.0 * Eps<double>::v * double(N * NXI) * 20.0, 0.01 * o.tol_eq);
         double a = ap;
         int nbt = 0;
-        double ft, tht, lst, reqt;
+        double ft, tht, lst, reqt, rst;
         for (;;) {
-            s.evaluate(a, ft, tht, lst, reqt);
+            s.evaluate(a, ft, tht, lst, reqt, rst);
             __syncwarp();
             const double pht = ft - mu_t * lst;
             const bool acc = (tht <= fmax((1.0 - 1e-5) * th_cur, th_noise)) ||
@@ -499,8 +517,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
         }
         nbt_total += nbt;
         alpha_p = a; alpha_d = ad;
-        s.update(mu_t, a, ad);
-        f_cur = ft; th_cur = tht; ls_cur = lst; req_n = reqt;
+        s.update_primal(a);
+        f_cur = ft; th_cur = tht; ls_cur = lst; req_n = reqt; rs_n = rst;
         __syncwarp();
     }
 

@@ -8,13 +8,19 @@ for r in rows:
     if not r: continue
     if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
     if r[0] == "Function Name": continue
-    if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; continue
+    if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; ncol = len(r); continue
     if hdr and r[0] not in ("", "-"):
         try:
             ln = int(r[0])
         except ValueError:
             continue
-        fl = lambda x: float(x) if x not in ("", "-") else 0.0
+        def fl(x):
+            try:
+                return float(x)
+            except ValueError:
+                return 0.0
+        if len(r) != ncol:
+            continue
         ie = fl(r[hdr["Instructions Executed"]]); sm = fl(r[hdr["# Samples"]])
         lines.append((cur_file, ln, r[1].strip()[:90], ie, sm))
 ti = sum(l[3] for l in lines); ts = sum(l[4] for l in lines)
