@@ -34,7 +34,7 @@ EXPORTS = [
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",
     "nmpc_backsolve_algorithmic_bytes",
     "nmpc_pack_params_f64", "nmpc_shift_warm_start_f64", "nmpc_wrap_yaw_f64", "nmpc_sample_reference_f64", "nmpc_default_ellipsoid_consts", "nmpc_propagate_ellipsoids_f64", "nmpc_select_corridors_f64",
-    "nmpc_fma_peak_probe",
+    "nmpc_fma_peak_probe", "nmpc_adopt_plans_f64", "nmpc_rank_longest_first",
     "FORCESNLPsolver_normal_solve", "FORCESNLPsolver_final_solve",
 ]
 

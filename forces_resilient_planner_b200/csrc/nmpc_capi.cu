@@ -5,6 +5,8 @@
 // that plan_manage/src/forces_normal.cpp:139 and forces_final.cpp:138 call.  No CPU fallback
 // exists anywhere in this file: every path ends in the sm_100a kernel or in an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <chrono>
 #include <cmath>
@@ -328,12 +330,83 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     return 0;
 }
 
+// ---- end-of-batch collation over NCCL (north star: "NCCL all-gather only for the end-of-batch result
+// collation") -------------------------------------------------------------------------------------------------------
+// libnccl is resolved at run time (dlopen "libnccl.so.2": the copy already in the process -- e.g. the one torch brought
+// -- or the system's), so single-GPU users carry no NCCL dependency and the library never mixes two NCCL builds' handles.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*MemAlloc)(void**, size_t) = nullptr;            // optional (NCCL >= 2.19)
+    ncclResult_t (*MemFree)(void*) = nullptr;
+    ncclResult_t (*CommRegister)(const ncclComm_t, void*, size_t, void**) = nullptr;
+    ncclResult_t (*CommDeregister)(const ncclComm_t, void*) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+std::mutex g_nccl_mutex;
+NcclApi g_nccl;
+
+int nccl_api(NcclApi** out)
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (!g_nccl.h) {
+        const char* env = getenv("NMPC_B200_NCCL");
+        void* h = dlopen(env && env[0] ? env : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(NMPC_ERR_CUDA, "cannot load libnccl.so.2: %s (set NMPC_B200_NCCL)", dlerror());
+        NcclApi a;
+        a.h = h;
+#define NMPC_NCCL_SYM(field, name, required)                                                       \
+        a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name));                             \
+        if (required && !a.field) return fail(NMPC_ERR_CUDA, "libnccl lacks %s", name);
+        NMPC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId", true)
+        NMPC_NCCL_SYM(CommInitRank, "ncclCommInitRank", true)
+        NMPC_NCCL_SYM(CommDestroy, "ncclCommDestroy", true)
+        NMPC_NCCL_SYM(AllGather, "ncclAllGather", true)
+        NMPC_NCCL_SYM(GroupStart, "ncclGroupStart", true)
+        NMPC_NCCL_SYM(GroupEnd, "ncclGroupEnd", true)
+        NMPC_NCCL_SYM(GetErrorString, "ncclGetErrorString", true)
+        NMPC_NCCL_SYM(GetVersion, "ncclGetVersion", true)
+        NMPC_NCCL_SYM(MemAlloc, "ncclMemAlloc", false)
+        NMPC_NCCL_SYM(MemFree, "ncclMemFree", false)
+        NMPC_NCCL_SYM(CommRegister, "ncclCommRegister", false)
+        NMPC_NCCL_SYM(CommDeregister, "ncclCommDeregister", false)
+#undef NMPC_NCCL_SYM
+        g_nccl = a;
+    }
+    *out = &g_nccl;
+    return 0;
+}
+
+#define NCCL_TRY(api, expr)                                                                        \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        if (_r != ncclSuccess) return fail(NMPC_ERR_CUDA, "%s failed: %s", #expr, (api)->GetErrorString(_r)); \
+    } while (0)
+
+}  // namespace
+
+struct nmpc_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    bool owned = true;
+    struct Reg { void* ptr; void* handle; bool nccl_mem; };
+    std::vector<Reg> regs;
+};
+
+namespace {
+
 // ---- reference ABI shim ------------------------------------------------------------------------
 // Unpacks the 130-slot per-stage parameter layout (matlab_code/setup.m:60-66) into the native one.
 // All-zero padding rows (forces_normal.cpp:127-135: A = 0, b = 0, i.e. the constant 0 <= 1e-5)
 // carry no information and are dropped.
 int forces_solve(const double* xinit, const double* x0, const double* allp, double* out340,
-                 int variant, int* it, int* nbt, double ir[8], double* seconds)
+                 int variant, int* it, int* nbt, double ir[8], double* seconds, int* n_ineq)
 {
     constexpr int N = 20;
     auto t0 = std::chrono::steady_clock::now();
@@ -364,26 +437,45 @@ int forces_solve(const double* xinit, const double* x0, const double* allp, doub
     int rc = solve_host(1, N, mcap, xinit, x0, hdr.data(), rows.data(), nrows.data(), variant, nullptr,
                         out340, ii, ir, sizeof(double), false);
     *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc) return rc == NMPC_ERR_ARG ? -11 : rc;
+    // inequalities of the problem as solved: two bound sides per free variable + the live corridor rows of stages 1..N-1
+    *n_ineq = 2 * (8 + (N - 1) * 17);
+    for (int k = 1; k < N; k++) *n_ineq += nrows[k];
+    // library failures in the reference's own vocabulary (header :110-139): a bad argument is PARAM_VALUE_ERROR (-11);
+    // "no CUDA device / CUDA runtime failure" has no counterpart but LICENSE_ERROR (-100, "solver not valid on this
+    // machine"), which the planner treats like any other failure (nmpc_solver.cpp:398-421).  nmpc_last_error() has the text.
+    if (rc) return rc == NMPC_ERR_ARG ? PARAM_VALUE_ERROR_FORCESNLPsolver_normal : LICENSE_ERROR_FORCESNLPsolver_normal;
     *it = ii[1]; *nbt = ii[2];
     return ii[0];
 }
 
 template <typename Info>
-void fill_info(Info* info, int it, int nbt, const double ir[8], double seconds)
+void fill_info(Info* info, int it, int nbt, const double ir[8], double seconds, int n_ineq)
 {
     if (!info) return;
-    const double n_ineq = 2 * (8 + 19 * 17);   // bound pairs; corridor rows vary, reported via mu
+    nmpc_opts o;
+    nmpc_default_opts(&o);
     info->it = it; info->it2opt = it;
     info->res_eq = ir[0]; info->res_ineq = ir[1]; info->rsnorm = ir[2]; info->rcompnorm = ir[3];
     info->pobj = ir[4];
     info->dgap = ir[5] * n_ineq;
     info->dobj = ir[4] - info->dgap;
     info->rdgap = ir[4] != 0.0 ? std::fabs(info->dgap / ir[4]) : 0.0;
-    info->mu = ir[5]; info->mu_aff = ir[5]; info->sigma = 0.1;
+    info->mu = ir[5]; info->mu_aff = ir[5]; info->sigma = o.sigma;
     info->lsit_aff = 0; info->lsit_cc = nbt;
     info->step_aff = ir[7]; info->step_cc = ir[6];
     info->solvetime = seconds; info->fevalstime = 0.0;
+}
+
+template <typename Params, typename Output, typename Info>
+int forces_entry(Params* params, Output* output, Info* info, FILE* fs, int variant)
+{
+    if (!params || !output) return PARAM_VALUE_ERROR_FORCESNLPsolver_normal;
+    int it = 0, nbt = 0, n_ineq = 0; double ir[8] = {0}, sec = 0;
+    const int flag = forces_solve(params->xinit, params->x0, params->all_parameters, output->x01, variant, &it, &nbt, ir, &sec, &n_ineq);
+    fill_info(info, it, nbt, ir, sec, n_ineq);
+    if (fs) fprintf(fs, "FORCESNLPsolver_%s (nmpc_b200): exitflag %d, it %d, pobj %.6e, res_eq %.2e, rsnorm %.2e, time %.3e s%s%s\n",
+                    variant ? "final" : "normal", flag, it, ir[4], ir[0], ir[2], sec, flag <= -100 ? " -- " : "", flag <= -100 ? g_err : "");
+    return flag;
 }
 
 // ---- device model probe (tests): evaluates the device model exactly as the solver does -----------
@@ -545,6 +637,142 @@ int nmpc_solve_batch_host_mixed_f64(int B, int N, int mcap, const double* xinit,
     return solve_host(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, 8, true);
 }
 
+/* ---- multi-GPU: contiguous sharding + end-of-batch NCCL all-gather ---------------------------------------------- */
+int nmpc_comm_unique_id(char id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (!id) return fail(NMPC_ERR_ARG, "null pointer argument");
+    ncclUniqueId u;
+    NCCL_TRY(api, api->GetUniqueId(&u));
+    std::memcpy(id, &u, 128);
+    return 0;
+}
+int nmpc_comm_create(int world, int rank, const char id[128], nmpc_comm** out)
+{
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(NMPC_ERR_ARG, "bad argument: world=%d rank=%d", world, rank);
+    ncclUniqueId u;
+    std::memcpy(&u, id, 128);
+    nmpc_comm* c = new nmpc_comm;
+    c->rank = rank; c->world = world; c->owned = true;
+    ncclResult_t r = api->CommInitRank(&c->comm, world, u, rank);
+    if (r != ncclSuccess) { delete c; return fail(NMPC_ERR_CUDA, "ncclCommInitRank failed: %s", api->GetErrorString(r)); }
+    *out = c;
+    return 0;
+}
+int nmpc_comm_wrap(void* nccl_comm, int world, int rank, nmpc_comm** out)
+{
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world) return fail(NMPC_ERR_ARG, "bad argument");
+    nmpc_comm* c = new nmpc_comm;
+    c->comm = static_cast<ncclComm_t>(nccl_comm); c->rank = rank; c->world = world; c->owned = false;
+    *out = c;
+    return 0;
+}
+int nmpc_comm_rank(const nmpc_comm* c) { return c ? c->rank : -1; }
+int nmpc_comm_world(const nmpc_comm* c) { return c ? c->world : -1; }
+int nmpc_comm_nccl_version(void)
+{
+    NcclApi* api;
+    if (nccl_api(&api)) return -1;
+    int v = 0;
+    return api->GetVersion(&v) == ncclSuccess ? v : -1;
+}
+int nmpc_comm_alloc(nmpc_comm* c, size_t bytes, void** ptr)
+{
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (!c || !ptr || bytes == 0) return fail(NMPC_ERR_ARG, "bad argument");
+    nmpc_comm::Reg reg{nullptr, nullptr, false};
+    if (api->MemAlloc && api->MemFree && api->MemAlloc(&reg.ptr, bytes) == ncclSuccess) reg.nccl_mem = true;
+    else CUDA_TRY(cudaMalloc(&reg.ptr, bytes));
+    // user-buffer registration: NCCL then reads / writes this buffer directly (no staging copy; NVLS-eligible)
+    if (api->CommRegister && api->CommRegister(c->comm, reg.ptr, bytes, &reg.handle) != ncclSuccess) reg.handle = nullptr;
+    c->regs.push_back(reg);
+    *ptr = reg.ptr;
+    return 0;
+}
+int nmpc_comm_free(nmpc_comm* c, void* ptr)
+{
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (!c || !ptr) return fail(NMPC_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < c->regs.size(); i++)
+        if (c->regs[i].ptr == ptr) {
+            if (c->regs[i].handle && api->CommDeregister) api->CommDeregister(c->comm, c->regs[i].handle);
+            if (c->regs[i].nccl_mem) api->MemFree(ptr); else cudaFree(ptr);
+            c->regs.erase(c->regs.begin() + i);
+            return 0;
+        }
+    return fail(NMPC_ERR_ARG, "pointer was not allocated by nmpc_comm_alloc");
+}
+int nmpc_comm_destroy(nmpc_comm* c)
+{
+    if (!c) return 0;
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    while (!c->regs.empty()) nmpc_comm_free(c, c->regs.back().ptr);
+    if (c->owned && c->comm) api->CommDestroy(c->comm);
+    delete c;
+    return 0;
+}
+
+// in-place all-gather of every rank's slice (sendbuff = recvbuff + rank * count): results land where the kernel wrote them
+static int collate_inplace(nmpc_comm* c, void* z_all, size_t z_bytes_per_rank, int* info_all, size_t info_ints_per_rank, cudaStream_t st)
+{
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (c->world == 1) return 0;
+    NCCL_TRY(api, api->GroupStart());
+    ncclResult_t r1 = api->AllGather(static_cast<char*>(z_all) + (size_t)c->rank * z_bytes_per_rank, z_all, z_bytes_per_rank, ncclChar, c->comm, st);
+    ncclResult_t r2 = info_all ? api->AllGather(info_all + (size_t)c->rank * info_ints_per_rank, info_all, info_ints_per_rank, ncclInt, c->comm, st)
+                               : ncclSuccess;
+    ncclResult_t r3 = api->GroupEnd();
+    if (r1 != ncclSuccess || r2 != ncclSuccess || r3 != ncclSuccess)
+        return fail(NMPC_ERR_CUDA, "ncclAllGather failed: %s", api->GetErrorString(r1 != ncclSuccess ? r1 : (r2 != ncclSuccess ? r2 : r3)));
+    return 0;
+}
+
+static int solve_sharded(nmpc_comm* c, int B_local, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+                         const int* nrows, int variant, const nmpc_opts* opts, void* z_all, int* info_int_all, void* info_real_local,
+                         void* stream, size_t esz, bool mixed)
+{
+    if (!c || !z_all || !info_int_all) return fail(NMPC_ERR_ARG, "null pointer argument");
+    if (B_local < 0) return fail(NMPC_ERR_ARG, "B_local < 0");
+    const size_t zb = (size_t)B_local * N * 17 * esz, ib = (size_t)B_local * 4;
+    if ((zb & 15) != 0) return fail(NMPC_ERR_ARG, "B_local must keep every rank's slice 16-byte aligned (even B_local)");
+    char* z_mine = static_cast<char*>(z_all) + (size_t)c->rank * zb;
+    int* ii_mine = info_int_all + (size_t)c->rank * ib;
+    int rc = mixed ? solve_mixed(B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_mine, ii_mine, info_real_local, stream, esz == 4)
+                   : solve_device(B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_mine, ii_mine, info_real_local, stream);
+    if (rc) return rc;
+    return collate_inplace(c, z_all, zb, info_int_all, ib, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nmpc_solve_batch_sharded_f64(nmpc_comm* comm, int B_local, int N, int mcap, const double* xinit, const double* z0,
+                                 const double* hdr, const double* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                                 double* z_all, int* info_int_all, double* info_real_local, int mixed, void* cuda_stream)
+{
+    return solve_sharded(comm, B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_all, info_int_all, info_real_local,
+                         cuda_stream, 8, mixed != 0);
+}
+int nmpc_solve_batch_sharded_f32(nmpc_comm* comm, int B_local, int N, int mcap, const float* xinit, const float* z0,
+                                 const float* hdr, const float* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                                 float* z_all, int* info_int_all, float* info_real_local, void* cuda_stream)
+{
+    return solve_sharded(comm, B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_all, info_int_all, info_real_local,
+                         cuda_stream, 4, true);
+}
+int nmpc_collate_inplace(nmpc_comm* comm, void* buf_all, size_t bytes_per_rank, void* cuda_stream)
+{
+    if (!comm || !buf_all) return fail(NMPC_ERR_ARG, "null pointer argument");
+    return collate_inplace(comm, buf_all, bytes_per_rank, nullptr, 0, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 int nmpc_backsolve_factor_words(void) { return nmpc::FAC_WORDS; }
 long nmpc_backsolve_algorithmic_bytes(int N, int elem_size) { return (long)N * (nmpc::FAC_WORDS + 2 * (17 + 13)) * elem_size; }
 
@@ -669,6 +897,29 @@ int nmpc_shift_warm_start_f64(int B, int N, const double* z_prev, double* xinit,
     return 0;
 }
 
+int nmpc_adopt_plans_f64(int B, int N, const double* z_new, const int* info_int, const int* accept, const double* odom,
+                         double* z_prev, int* cold, int wrap_yaw, void* stream)
+{
+    if (B < 0 || N <= 1 || N > 256) return fail(NMPC_ERR_ARG, "bad argument: B=%d N=%d", B, N);
+    if (B == 0) return 0;
+    if (!z_new || !z_prev || (!info_int && !accept)) return fail(NMPC_ERR_ARG, "null pointer argument");
+    const int apb = 256 / N > 0 ? 256 / N : 1;                       // whole agents per block
+    nmpc::adopt_plans_kernel<<<(B + apb - 1) / apb, apb * N, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        B, N, z_new, info_int, accept, odom, z_prev, cold, wrap_yaw);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nmpc_rank_longest_first(int B, const int* info_int, int* order, void* stream)
+{
+    if (B < 0 || B > 12288) return fail(NMPC_ERR_ARG, "bad argument: B=%d (one CTA ranks at most 12288 agents)", B);
+    if (B == 0) return 0;
+    if (!info_int || !order) return fail(NMPC_ERR_ARG, "null pointer argument");
+    nmpc::rank_longest_first_kernel<<<1, 1024, (size_t)B * sizeof(int), reinterpret_cast<cudaStream_t>(stream)>>>(B, info_int, order);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int nmpc_model_eval_host_f64(int n, const double* z, const double* p, const int* stage, int n_stages, int variant,
                              double* f, double* grad, double* c, double* jc, double* h, double* jh)
 {
@@ -696,32 +947,30 @@ int nmpc_model_eval_host_f64(int n, const double* z, const double* p, const int*
 }
 
 // ---- the reference's solver symbols ---------------------------------------------------------------
-solver_int32_default FORCESNLPsolver_normal_solve(FORCESNLPsolver_normal_params* params,
-                                                  FORCESNLPsolver_normal_output* output,
+// Each exists under two names bound to one internal function: the reference's own name (a planner that links
+// libnmpc_b200.so directly) and a library-private one (what the stub archives libFORCESNLPsolver_{normal,final}.a,
+// host/forces_stub.c, resolve with dlsym -- the stub itself defines the reference name in the executable, and symbol
+// interposition must not send the library's call back into it).
+solver_int32_default FORCESNLPsolver_normal_solve(FORCESNLPsolver_normal_params* params, FORCESNLPsolver_normal_output* output,
                                                   FORCESNLPsolver_normal_info* info, FILE* fs,
                                                   FORCESNLPsolver_normal_extfunc /*ignored: device model built in*/)
 {
-    if (!params || !output) return PARAM_VALUE_ERROR_FORCESNLPsolver_normal;
-    int it = 0, nbt = 0; double ir[8] = {0}, sec = 0;
-    int flag = forces_solve(params->xinit, params->x0, params->all_parameters, output->x01, 0, &it, &nbt, ir, &sec);
-    fill_info(info, it, nbt, ir, sec);
-    if (fs) fprintf(fs, "FORCESNLPsolver_normal (nmpc_b200): exitflag %d, it %d, pobj %.6e, res_eq %.2e, rsnorm %.2e, time %.3e s%s%s\n",
-                    flag, it, ir[4], ir[0], ir[2], sec, flag <= -100 ? " -- " : "", flag <= -100 ? g_err : "");
-    return flag;
+    return forces_entry<FORCESNLPsolver_normal_params, FORCESNLPsolver_normal_output, FORCESNLPsolver_normal_info>(params, output, info, fs, 0);
 }
-
-solver_int32_default FORCESNLPsolver_final_solve(FORCESNLPsolver_final_params* params,
-                                                 FORCESNLPsolver_final_output* output,
-                                                 FORCESNLPsolver_final_info* info, FILE* fs,
-                                                 FORCESNLPsolver_final_extfunc /*ignored*/)
+solver_int32_default nmpc_forces_normal_solve(FORCESNLPsolver_normal_params* params, FORCESNLPsolver_normal_output* output,
+                                              FORCESNLPsolver_normal_info* info, FILE* fs, FORCESNLPsolver_normal_extfunc)
 {
-    if (!params || !output) return PARAM_VALUE_ERROR_FORCESNLPsolver_final;
-    int it = 0, nbt = 0; double ir[8] = {0}, sec = 0;
-    int flag = forces_solve(params->xinit, params->x0, params->all_parameters, output->x01, 1, &it, &nbt, ir, &sec);
-    fill_info(info, it, nbt, ir, sec);
-    if (fs) fprintf(fs, "FORCESNLPsolver_final (nmpc_b200): exitflag %d, it %d, pobj %.6e, res_eq %.2e, rsnorm %.2e, time %.3e s%s%s\n",
-                    flag, it, ir[4], ir[0], ir[2], sec, flag <= -100 ? " -- " : "", flag <= -100 ? g_err : "");
-    return flag;
+    return forces_entry<FORCESNLPsolver_normal_params, FORCESNLPsolver_normal_output, FORCESNLPsolver_normal_info>(params, output, info, fs, 0);
+}
+solver_int32_default FORCESNLPsolver_final_solve(FORCESNLPsolver_final_params* params, FORCESNLPsolver_final_output* output,
+                                                 FORCESNLPsolver_final_info* info, FILE* fs, FORCESNLPsolver_final_extfunc /*ignored*/)
+{
+    return forces_entry<FORCESNLPsolver_final_params, FORCESNLPsolver_final_output, FORCESNLPsolver_final_info>(params, output, info, fs, 1);
+}
+solver_int32_default nmpc_forces_final_solve(FORCESNLPsolver_final_params* params, FORCESNLPsolver_final_output* output,
+                                             FORCESNLPsolver_final_info* info, FILE* fs, FORCESNLPsolver_final_extfunc)
+{
+    return forces_entry<FORCESNLPsolver_final_params, FORCESNLPsolver_final_output, FORCESNLPsolver_final_info>(params, output, info, fs, 1);
 }
 
 }  // extern "C"

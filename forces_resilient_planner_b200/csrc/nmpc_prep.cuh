@@ -59,9 +59,14 @@ __global__ void pack_params_kernel(const PackParams q)
     h[7] = terminal ? q.w_terminal_input : q.w_stage_input;
     h[8] = q.w_input_rate;
     h[9] = q.ref_yaw[t];
-    const int pi = q.poly_idx[t];
-    const int m_poly = q.poly_m[b * q.P + pi];
-    const int m = m_poly < q.mcap ? m_poly : q.mcap;
+    // a polytope index outside [0, P) or a row count beyond the allocated M would read past poly_A / poly_b and
+    // hand the solver garbage as safety constraints: clamp both (the reference's own truncation is at 30 rows, :114)
+    int pi = q.poly_idx[t];
+    pi = pi < 0 ? 0 : (pi >= q.P ? q.P - 1 : pi);
+    int m = q.poly_m[b * q.P + pi];
+    m = m < 0 ? 0 : m;
+    m = m < q.M ? m : q.M;
+    m = m < q.mcap ? m : q.mcap;
     const double* E = q.ellipsoid + (size_t)t * 9;
     const double* A = q.poly_A + ((size_t)b * q.P + pi) * q.M * 3;
     const double* bb = q.poly_b + ((size_t)b * q.P + pi) * q.M;
@@ -106,6 +111,63 @@ __global__ void wrap_yaw_kernel(int n_stages_total, double* z)
     if (t >= n_stages_total) return;
     const double v = z[(size_t)t * 17 + 16];
     z[(size_t)t * 17 + 16] = v < -REF_PI ? v + 2 * REF_PI : (v > REF_PI ? v - 2 * REF_PI : v);
+}
+
+// Result handling of NMPCSolver::solveNMPC (nmpc_solver.cpp:398-427, 363-364): the new plan replaces the previous
+// one only when it is accepted (exit flag 1, or the caller's acceptance mask -- the "tolerate MAXIT after more than 3
+// replans" rule is host policy, SolveAcceptance); a rejected agent keeps nothing of the failed solve (its output may be
+// NaN) and cold-starts on the next cycle exactly as initMPCOutput does (:265-286): every stage = [0,0,0,7.3, 0,0,0,7.3,
+// x] with x its current state -- `odom` when the caller has one, otherwise where the previous plan puts the vehicle one
+// period later (its stage 2, the plan having been adopted one period ago).  Adopted plans are stored yaw-wrapped
+// (updateFORCESResults, :531-541).  One thread per (agent, stage).
+// Launch with blockDim.x = N * (agents per block): an agent never straddles two blocks, so one barrier separates every
+// read of its old plan from the writes that replace it.
+__global__ void adopt_plans_kernel(int B, int N, const double* z_new, const int* info_int, const int* accept, const double* odom,
+                                   double* z_prev, int* cold, int wrap_yaw)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < B * N;
+    const int b = live ? t / N : 0, i = live ? t - b * N : 0;
+    const bool ok = accept ? accept[b] != 0 : info_int[(size_t)b * 4] == 1;
+    double x[9];
+    if (live && !ok) {
+        const double* src = odom ? odom + (size_t)b * 9 : z_prev + ((size_t)b * N + (N > 2 ? 2 : N - 1)) * 17 + 8;
+        for (int j = 0; j < 9; j++) x[j] = src[j];
+    }
+    __syncthreads();
+    if (!live) return;
+    double* zp = z_prev + (size_t)t * 17;
+    if (ok) {
+        const double* zn = z_new + (size_t)t * 17;
+        for (int j = 0; j < 16; j++) zp[j] = zn[j];
+        const double v = zn[16];
+        zp[16] = !wrap_yaw ? v : (v < -REF_PI ? v + 2 * REF_PI : (v > REF_PI ? v - 2 * REF_PI : v));
+    } else {
+        zp[0] = zp[1] = zp[2] = 0.0; zp[3] = 7.3; zp[4] = zp[5] = zp[6] = 0.0; zp[7] = 7.3;
+        for (int j = 0; j < 9; j++) zp[8 + j] = x[j];
+    }
+    if (i == 0 && cold) cold[b] = ok ? 0 : 1;
+}
+
+// order[r] = index of the agent with the r-th largest key, key = iterations of the last solve (+1000 for a failed one),
+// ties by agent index: the launch order of the next warm solve (longest first, see nmpc_solve_batch_ordered_f64).
+// One CTA, one thread per agent (B <= 1024 per CTA tile; larger fleets loop): a rank count, O(B^2 / threads) compares
+// out of shared memory -- 1024 agents: 1 M compares, a few microseconds; no library sort on the replan path.
+__global__ void rank_longest_first_kernel(int B, const int* info_int, int* order)
+{
+    extern __shared__ int keys[];
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+        keys[b] = info_int[(size_t)b * 4 + 1] + (info_int[(size_t)b * 4] != 1 ? 1000 : 0);
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int kb = keys[b];
+        int rank = 0;
+        for (int c = 0; c < B; c++) {
+            const int kc = keys[c];
+            rank += (kc > kb) || (kc == kb && c < b);
+        }
+        order[rank] = b;
+    }
 }
 
 struct SampleParams {

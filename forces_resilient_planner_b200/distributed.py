@@ -1,72 +1,162 @@
 """Multi-GPU driver: contiguous sharding of independent problems, one process per GPU.
 
-The NMPC instances never interact (single-vehicle planner), so the solve itself
-needs NO collective: rank r owns problems [r*B/G, (r+1)*B/G) and runs the same fused kernel on
-them.  The only exchange is the optional end-of-batch collation of results (z, exit flags,
-iteration counts) -- one all_gather over NCCL/NVLink, outside the solve.
+The NMPC instances never interact (single-vehicle planner), so the solve itself needs NO collective:
+rank r owns problems [r*per, (r+1)*per) with per = ceil(B / world) and runs the same fused kernel on them.  The only
+exchange is the end-of-batch collation of the results, and it is copy-free: every rank's kernel writes its z straight
+into its slice of ONE buffer of world*per problems and an in-place all-gather (sendbuff = recvbuff + rank*count) on the
+same stream completes the other slices -- `nmpc_solve_batch_sharded_{f64,f32}` of the C ABI (include/nmpc_b200.h), which
+drives NCCL itself.  torch.distributed is used for one thing only: handing rank 0's 128-byte NCCL id to the other ranks.
+
+`TorchCollator` is the same in-place gather through torch.distributed (any backend): it exists so that the host logic
+(shard arithmetic, slice placement, trimming of the padded tail) is testable with `gloo` on CPU, world size 2.
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
+from . import _lib
+from .solver import _check
 from .workloads import Batch
 
 
+def per_rank(B: int, world: int) -> int:
+    """Problems per rank: ceil(B / world), rounded up to even so that every rank's slice stays 16-byte aligned
+    (TMA bulk stores of the results) in fp32 and fp64 alike."""
+    per = -(-B // world)
+    return per + (per & 1)
+
+
 def shard_range(B: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous split; the first B % world ranks take one extra problem."""
-    base, extra = divmod(B, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    """Contiguous split in equal blocks of per_rank(B, world); the last rank(s) may be short (or empty)."""
+    per = per_rank(B, world)
+    lo = min(rank * per, B)
+    return lo, min(lo + per, B)
 
 
-def shard(batch: Batch, rank: int, world: int) -> Batch:
+def shard(batch: Batch, rank: int, world: int, pad: bool = False) -> Batch:
+    """This rank's problems.  pad=True repeats the last problem up to per_rank(B, world), so that every rank launches
+    the same grid and owns an equally sized slice of the collation buffer; the padding rows land beyond index B of the
+    gathered result and are never looked at."""
     lo, hi = shard_range(batch.B, rank, world)
-    return batch.slice(lo, hi)
+    if hi == lo:
+        lo, hi = batch.B - 1, batch.B                      # a rank with nothing to do solves a copy of the last problem
+    mine = batch.slice(lo, hi)
+    if pad:
+        need = per_rank(batch.B, world) - mine.B
+        if need > 0:
+            rep = lambda a: np.concatenate([a, np.repeat(a[-1:], need, axis=0)], axis=0)
+            mine = Batch(rep(mine.xinit), rep(mine.z0), rep(mine.hdr), rep(mine.rows), rep(mine.nrows), mine.variant)
+    return mine
 
 
-def all_gather_results(z_local, flag_local, it_local, B_total: int, group=None):
-    """Collate per-rank results into full-batch tensors on every rank.
+class NcclCollator:
+    """nmpc_comm of the C ABI: NCCL communicator + NCCL-registered result buffers.  One per process (= per GPU)."""
 
-    Inputs are torch tensors on the backend's device (cuda for nccl, cpu for gloo) holding this
-    rank's shard; shards may differ by one problem, so they are padded to the largest shard for
-    the fixed-size all_gather and trimmed afterwards."""
+    def __init__(self, rank: int, world: int, device, uid: bytes | None = None, group=None):
+        import torch
+        self.torch, self.lib = torch, _lib.load()
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        lib = self.lib
+        lib.nmpc_comm_unique_id.argtypes = [ctypes.c_char_p]
+        lib.nmpc_comm_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        lib.nmpc_comm_destroy.argtypes = [ctypes.c_void_p]
+        lib.nmpc_comm_alloc.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        lib.nmpc_comm_free.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.nmpc_collate_inplace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        sig = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + \
+            [ctypes.c_void_p] * 3
+        lib.nmpc_solve_batch_sharded_f64.argtypes = sig + [ctypes.c_int, ctypes.c_void_p]
+        lib.nmpc_solve_batch_sharded_f32.argtypes = sig + [ctypes.c_void_p]
+        if uid is None:
+            # the one use of torch.distributed: rank 0's NCCL id to everybody (a 128-byte broadcast over the existing group)
+            import torch.distributed as dist
+            buf = ctypes.create_string_buffer(128)
+            if rank == 0:
+                _check(lib.nmpc_comm_unique_id(buf))
+            box = [buf.raw]
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = box[0]
+        self.comm = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(lib.nmpc_comm_create(world, rank, uid, ctypes.byref(self.comm)))
+        self._bufs = []
+
+    def alloc(self, shape, dtype):
+        """A device tensor over NCCL-allocated, NCCL-registered memory (ncclMemAlloc + ncclCommRegister)."""
+        torch = self.torch
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self.lib.nmpc_comm_alloc(self.comm, n, ctypes.byref(ptr)))
+        self._bufs.append(ptr)
+        np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32}[dtype]
+
+        class _Mem:      # __cuda_array_interface__: torch wraps the memory without copying
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=np.dtype(np_dt).str, data=(ptr.value, False), version=3)
+        t = torch.as_tensor(m, device=self.device)
+        t._nmpc_owner = self          # keeps the communicator (and with it the allocation) alive
+        return t
+
+    def solve_sharded(self, db, z_all, info_int_all, opts=None, mixed: bool = False, stream=None):
+        """Enqueue solve + in-place all-gather for this rank's DeviceBatch `db` (every rank: the same db.B)."""
+        torch = self.torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        o = opts or _lib.default_opts()
+        d = db.d
+        args = [self.comm, db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
+                d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
+                z_all.data_ptr(), info_int_all.data_ptr(), db.info_real.data_ptr()]
+        with torch.cuda.device(self.device):
+            if db.np_dtype == np.float32:
+                _check(self.lib.nmpc_solve_batch_sharded_f32(*args, ctypes.c_void_p(st.cuda_stream)))
+            else:
+                _check(self.lib.nmpc_solve_batch_sharded_f64(*args, int(bool(mixed)), ctypes.c_void_p(st.cuda_stream)))
+
+    def collate(self, buf_all, stream=None):
+        torch = self.torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        per_bytes = buf_all.numel() * buf_all.element_size() // self.world
+        with torch.cuda.device(self.device):
+            _check(self.lib.nmpc_collate_inplace(self.comm, buf_all.data_ptr(), per_bytes, ctypes.c_void_p(st.cuda_stream)))
+
+    def close(self):
+        if self.comm:
+            self.torch.cuda.synchronize(self.device)
+            self.lib.nmpc_comm_destroy(self.comm)
+            self.comm = ctypes.c_void_p()
+
+
+class TorchCollator:
+    """The same in-place gather through torch.distributed (gloo on CPU in the tests, nccl on GPUs)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def collate(self, buf_all):
+        per = buf_all.shape[0] // self.world
+        self.dist.all_gather_into_tensor(buf_all, buf_all[self.rank * per:(self.rank + 1) * per], group=self.group)
+
+
+def solve_sharded(batch: Batch, local_solver, device, collator, dtype=np.float64):
+    """Solve `batch` across the ranks of `collator` and collate the results on every rank.
+
+    `local_solver(shard, z_out, info_out)` writes this rank's results into the two views it is given -- slices of the
+    collation buffers, so nothing is copied afterwards (the CUDA solver in production; the gloo tests inject a CPU
+    stand-in).  Returns (z [B,N,17], flag [B], it [B]) as views of the gathered buffers, trimmed to the true B."""
     import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    per = -(-B_total // world)
-    n_local = z_local.shape[0]
-
-    def pad(t):
-        if t.shape[0] == per:
-            return t.contiguous()
-        out = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        out[:n_local] = t
-        return out
-
-    outs = []
-    for t in (z_local, flag_local, it_local):
-        buf = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(buf, pad(t), group=group)
-        parts = []
-        for r in range(world):
-            lo, hi = shard_range(B_total, r, world)
-            parts.append(buf[r * per:r * per + (hi - lo)])
-        outs.append(torch.cat(parts, 0))
-    return tuple(outs)
-
-
-def solve_sharded(batch: Batch, local_solver, device, gather: bool = True, group=None):
-    """Solve `batch` across the process group.  `local_solver(shard) -> (z, flag, it)` numpy arrays
-    (the CUDA solver in production; tests inject a CPU stand-in to exercise the plumbing on gloo)."""
-    import torch
-    import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    mine = shard(batch, rank, world)
-    z, flag, it = local_solver(mine)
-    if not gather:
-        return z, flag, it
-    tz = torch.from_numpy(np.ascontiguousarray(z)).to(device)
-    tf = torch.from_numpy(np.ascontiguousarray(flag.astype(np.int32))).to(device)
-    ti = torch.from_numpy(np.ascontiguousarray(it.astype(np.int32))).to(device)
-    gz, gf, gi = all_gather_results(tz, tf, ti, batch.B, group)
-    return gz.cpu().numpy(), gf.cpu().numpy(), gi.cpu().numpy()
+    rank, world = collator.rank, collator.world
+    per = per_rank(batch.B, world)
+    mine = shard(batch, rank, world, pad=True)
+    t_dt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    z_all = torch.empty((world * per, batch.N, 17), dtype=t_dt, device=device)
+    info_all = torch.empty((world * per, 4), dtype=torch.int32, device=device)
+    local_solver(mine, z_all[rank * per:(rank + 1) * per], info_all[rank * per:(rank + 1) * per])
+    collator.collate(z_all)
+    collator.collate(info_all)
+    return z_all[:batch.B], info_all[:batch.B, 0], info_all[:batch.B, 1]

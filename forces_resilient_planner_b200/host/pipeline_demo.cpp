@@ -64,7 +64,8 @@ int main()
     nmpc_opts cold, warm;
     nmpc_default_opts(&cold); nmpc_default_opts(&warm); warm.mu0 = 0.1;
     std::vector<resilient_planner::SolveAcceptance> policy(B);
-    std::vector<int> ii((size_t)B * 4), ovf(B);
+    std::vector<int> ii((size_t)B * 4), ovf(B), accept(B);
+    int* d_accept = dev<int>((size_t)B);
     std::vector<double> zh((size_t)B * N * 17), toff(B);
     int bad = 0;
     for (int cycle = 0; cycle < 3; cycle++) {
@@ -85,7 +86,8 @@ int main()
         int ok = 0, itsum = 0, over = 0;
         double track = 0;
         for (int b = 0; b < B; b++) {
-            ok += policy[b].consume(ii[(size_t)b * 4]) ? 1 : 0;      // solveNMPC acceptance (:398-421)
+            accept[b] = policy[b].consume(ii[(size_t)b * 4]) ? 1 : 0;   // solveNMPC acceptance (:398-421)
+            ok += accept[b];
             itsum += ii[(size_t)b * 4 + 1]; over += ovf[b] != 0;
             const double* z1 = &zh[((size_t)b * N + 1) * 17];
             const double* p1 = &path[((size_t)b * P + cycle + 1) * 3];
@@ -94,8 +96,10 @@ int main()
         std::printf("cycle %d: %d/%d accepted, mean it %.2f, corridor overflow %d, max |pos1 - path| %.3f m\n", cycle, ok, B,
                     (double)itsum / B, over, track);
         bad += (B - ok) + over;
-        cudaMemcpy(d_zprev, d_z, zh.size() * sizeof(double), cudaMemcpyDeviceToDevice);   // updateNormal: adopt the plan
-        CHECK(nmpc_wrap_yaw_f64(B, N, d_zprev, nullptr));                                   // updateFORCESResults: keep it wrapped
+        // updateNormal / updateFORCESResults for the accepted agents only (kept yaw-wrapped); a rejected agent keeps
+        // nothing of the failed solve and restarts from the cold guess next cycle (:363-364)
+        cudaMemcpy(d_accept, accept.data(), B * sizeof(int), cudaMemcpyHostToDevice);
+        CHECK(nmpc_adopt_plans_f64(B, N, d_z, d_ii, d_accept, nullptr, d_zprev, nullptr, 1, nullptr));
     }
     return bad;
 }

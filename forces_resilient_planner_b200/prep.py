@@ -53,6 +53,37 @@ def shift_warm_start(z_prev, xinit=None, z0=None, wrap_yaw=True, stream=None):
     return xinit, z0
 
 
+def adopt_plans(z_new, info_int, z_prev, accept=None, odom=None, wrap_yaw=True, cold=None, stream=None):
+    """nmpc_adopt_plans_f64: accepted agents adopt z_new into z_prev (in place), rejected ones get the cold guess at
+    their current state (NMPCSolver::solveNMPC result handling, nmpc_solver.cpp:398-427, 363-364).
+    cold [B] (int32 cuda tensor, optional) receives 1 for the rejected agents; returned as given."""
+    import torch
+    lib = _lib.load()
+    B, N, _ = z_prev.shape
+    fn = lib.nmpc_adopt_plans_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p]
+    st = stream if stream is not None else torch.cuda.current_stream(z_prev.device)
+    with torch.cuda.device(z_prev.device):
+        _check(fn(B, N, z_new.data_ptr(), info_int.data_ptr() if info_int is not None else None,
+                  accept.data_ptr() if accept is not None else None, odom.data_ptr() if odom is not None else None,
+                  z_prev.data_ptr(), cold.data_ptr() if cold is not None else None, int(bool(wrap_yaw)), st.cuda_stream))
+    return cold
+
+
+def rank_longest_first(info_int, order, stream=None):
+    """nmpc_rank_longest_first: order [B] (int32, cuda) <- launch order of the next warm solve."""
+    import torch
+    lib = _lib.load()
+    fn = lib.nmpc_rank_longest_first
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    st = stream if stream is not None else torch.cuda.current_stream(info_int.device)
+    with torch.cuda.device(info_int.device):
+        _check(fn(info_int.shape[0], info_int.data_ptr(), order.data_ptr(), st.cuda_stream))
+    return order
+
+
 def sample_reference(kino_path, kino_size, t_off, last_yaw, N, Ts, pos1=None, stream=None):
     """Batched getCurTraj + calculate_yaw (nmpc_solver.cpp:109-142, 834-862) on the device.
 

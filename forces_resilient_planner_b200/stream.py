@@ -10,8 +10,9 @@ One replan = the reference's solveNMPC sequence for every agent at once
                        (setFORCESParams, nmpc_solver.cpp:484-521)            nmpc_propagate_ellipsoids_f64
     pack parameters    refs, f_ext, yaw refs, tightened corridor rows
                        (forces_normal.cpp:100-136)                          nmpc_pack_params_f64
-    solve              FORCESNLPsolver_normal_solve for every agent          nmpc_solve_batch_f64
-    failure policy     exit flag != 1 -> that agent cold-starts next cycle   (nmpc_solver.cpp:363-364)
+    solve              FORCESNLPsolver_normal_solve for every agent          nmpc_solve_batch_ordered_f64
+    result handling    exit flag 1 -> the plan is adopted; otherwise the agent keeps nothing of the failed
+                       solve and cold-starts next cycle (nmpc_solver.cpp:398-427, 363-364)   nmpc_adopt_plans_f64
 
 With a perfect-model plant the next initial state is the predicted stage-1 state, exactly what the
 reference feeds back (`xinit = mpc_output[1][8:17]`, not odometry).  The three launches of a replan
@@ -46,6 +47,7 @@ class RecedingHorizonStream:
         self.ref_pos = t(batch.hdr[:, :, 0:3]); self.ref_yaw = t(batch.hdr[:, :, 9]); self.ext_acc = t(batch.hdr[:, 0, 3:6])
         # solver state on the device
         self.xinit = t(batch.xinit); self.z0 = t(batch.z0); self.z = torch.empty_like(self.z0)
+        self.zprev = self.z0.clone()      # the plan in force (mpc_output_): only ACCEPTED solves ever enter it
         self.hdr = torch.empty((self.B, self.N, 10), dtype=torch.float64, device=self.dev)
         self.rows = torch.empty((self.B, self.N, self.mcap, 4), dtype=torch.float64, device=self.dev)
         self.nrows = torch.empty((self.B, self.N), dtype=torch.int32, device=self.dev)
@@ -78,9 +80,12 @@ class RecedingHorizonStream:
     def _enqueue(self, stream, warm: bool):
         torch = self.torch
         if warm:
-            prep.shift_warm_start(self.z, self.xinit, self.z0, wrap_yaw=self.wrap_yaw, stream=stream)
+            # result handling of the previous cycle, per agent: accepted plans are adopted, a failed solve (whose
+            # output may be NaN) leaves nothing behind -- that agent restarts from the cold guess at its state
+            prep.adopt_plans(self.z, self.info_int, self.zprev, wrap_yaw=False, stream=stream)
+            prep.shift_warm_start(self.zprev, self.xinit, self.z0, wrap_yaw=self.wrap_yaw, stream=stream)
         if self.dynamic_ellipsoids:
-            prep.propagate_ellipsoids(self.z if warm else self.z0, out=self.ellipsoid, stream=stream)
+            prep.propagate_ellipsoids(self.zprev if warm else self.z0, out=self.ellipsoid, stream=stream)
         hdr, rows, nrows = self.hdr, self.rows, self.nrows
         w = (ctypes.c_double * 5)(*self.weights)
         fn = self.lib.nmpc_pack_params_f64
@@ -93,9 +98,7 @@ class RecedingHorizonStream:
         o = self.opts_warm if warm else self.opts_cold
         order = None
         if warm and self.longest_first:
-            with torch.cuda.stream(stream):
-                key = self.info_int[:, 1] + 1000 * (self.info_int[:, 0] != 1).int()
-                self.order.copy_(torch.argsort(key, descending=True, stable=True))
+            prep.rank_longest_first(self.info_int, self.order, stream=stream)
             order = self.order.data_ptr()
         fn = self.lib.nmpc_solve_batch_ordered_f64
         fn.restype = ctypes.c_int
@@ -124,7 +127,8 @@ class RecedingHorizonStream:
             if self.graph is None:
                 torch.cuda.synchronize(self.dev)
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                # thread_local: other threads of the process (NCCL watchdogs, a sampler) may keep calling CUDA while we capture
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                     self._enqueue(torch.cuda.current_stream(self.dev), warm=True)
             self.graph.replay()
         self.cycle += 1
@@ -132,21 +136,6 @@ class RecedingHorizonStream:
         flag = self.info_int[:, 0].cpu().numpy()
         it = self.info_int[:, 1].cpu().numpy()
         return cmd, flag, it
-
-    def reset_failed(self, flag: np.ndarray):
-        """Reference failure policy: an agent whose solve failed cold-starts on the next cycle
-        (nmpc_solver.cpp:363-364): its trajectory is replaced by the hover guess at its current state."""
-        bad = np.nonzero(flag != 1)[0]
-        if bad.size:
-            torch = self.torch
-            idx = torch.from_numpy(bad).to(self.dev)
-            x = self.z[idx, 1, 8:17]
-            cold = torch.zeros((bad.size, self.N, 17), dtype=torch.float64, device=self.dev)
-            cold[:, :, 3] = W.HOVER_THRUST_GUESS; cold[:, :, 7] = W.HOVER_THRUST_GUESS
-            cold[:, :, 8:17] = x[:, None, :]
-            self.z[idx] = cold
-        return bad.size
-
 
 def synthetic_refs(batch: W.Batch, step: int, rng: np.random.Generator, ext_acc: np.ndarray, period: int = 20):
     """References of replan `step` for the config-2 style scenario: the straight-line reference
@@ -199,6 +188,8 @@ class PlannerPipeline:
         self.lib = _lib.load()
         self.cycle = 0
         self.last = {}
+        from . import forces
+        self.policy = [forces.SolveAcceptance() for _ in range(self.B)]   # solveNMPC's per-vehicle acceptance state
 
     def replan(self, ext_acc: np.ndarray, t_off: np.ndarray):
         """ext_acc [B,3], t_off [B] (= mpc_start_time_ - kino_start_time_) on the host -> (commands, flags, iterations)."""
@@ -224,9 +215,14 @@ class PlannerPipeline:
                                              z_new.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr(),
                                              ctypes.c_void_p(st.cuda_stream)))
         cmd = z_new[:, 0, 0:4].cpu().numpy()
-        prep.wrap_yaw(z_new, stream=st)                  # updateFORCESResults (:531-541): the adopted plan is kept wrapped
-        self.z = z_new
+        flag = self.info_int[:, 0].cpu().numpy()
+        # solveNMPC's result handling (:398-427): the acceptance policy is per-vehicle host state; only accepted plans
+        # are adopted (kept yaw-wrapped, updateFORCESResults :531-541), a rejected agent restarts cold next cycle
+        accept = np.array([p.consume(int(f)) for p, f in zip(self.policy, flag)], dtype=np.int32)
+        self.last_cold = prep.adopt_plans(z_new, self.info_int, self.z, accept=torch.from_numpy(accept).to(self.dev),
+                                          wrap_yaw=True, cold=torch.empty((self.B,), dtype=torch.int32, device=self.dev),
+                                          stream=st)
         self.cycle += 1
         self.last = dict(ellipsoid=E, ref_pos=ref_pos, ref_yaw=ref_yaw, hard_to_follow=far, poly_idx=pidx, n_poly=npoly,
                          overflow=ovf, hdr=hdr, rows=rows, nrows=nrows)
-        return cmd, self.info_int[:, 0].cpu().numpy(), self.info_int[:, 1].cpu().numpy()
+        return cmd, flag, self.info_int[:, 1].cpu().numpy()

@@ -18,7 +18,10 @@
 #ifndef FORCESNLPsolver_final_H
 #define FORCESNLPsolver_final_H
 
+#ifndef SOLVER_STDIO_H
+#define SOLVER_STDIO_H
 #include <stdio.h>
+#endif
 
 #ifndef SOLVER_STANDARD_TYPES
 #define SOLVER_STANDARD_TYPES
@@ -40,7 +43,34 @@ typedef double FORCESNLPsolver_final_float;
 typedef double FORCESNLPsolver_final_callback_float;
 typedef double FORCESNLPsolver_finalinterface_float;
 
+/* ---- solver settings the generated header publishes as macros (reference header :62-108); callers may test them.
+ * Values are the reference's.  Note SET_ACC_* are ForcesPro's QP-era defaults (1e-6); the NLP stopping test the
+ * solver was generated with -- and that this implementation uses -- is 1e-4 (mpc_generator_final.m:76-79). */
+#ifndef MISRA_C_FORCESNLPsolver_final
+#define MISRA_C_FORCESNLPsolver_final (0)
+#endif
+#ifndef RESTRICT_CODE_FORCESNLPsolver_final
+#define RESTRICT_CODE_FORCESNLPsolver_final (0)
+#endif
+#ifndef SET_PRINTLEVEL_FORCESNLPsolver_final
+#define SET_PRINTLEVEL_FORCESNLPsolver_final (1)      /* one summary line when the FILE* argument is non-NULL */
+#endif
+#ifndef SET_TIMING_FORCESNLPsolver_final
+#define SET_TIMING_FORCESNLPsolver_final (1)          /* info.solvetime is filled (wall clock of the call)    */
+#endif
 #define SET_MAXIT_FORCESNLPsolver_final (200)
+#define SET_FLS_SCALE_FORCESNLPsolver_final (FORCESNLPsolver_final_float)(0.99)
+#define MAX_FILTER_SIZE_FORCESNLPsolver_final (200)
+#define MAX_SOC_IT_FORCESNLPsolver_final (4)
+#define SET_ACC_RDGAP_FORCESNLPsolver_final (FORCESNLPsolver_final_float)(0.0001)
+#define SET_ACC_RESEQ_FORCESNLPsolver_final (FORCESNLPsolver_final_float)(1E-06)
+#define SET_ACC_RESINEQ_FORCESNLPsolver_final (FORCESNLPsolver_final_float)(1E-06)
+#define SET_ACC_KKTCOMPL_FORCESNLPsolver_final (FORCESNLPsolver_final_float)(1E-06)
+/* integrator return codes (reference header :141-145) */
+#ifndef INTEGRATOR_SUCCESS
+#define INTEGRATOR_SUCCESS (11)
+#define INTEGRATOR_MAXSTEPS_EXCEEDED (12)
+#endif
 #define OPTIMAL_FORCESNLPsolver_final (1)
 #define MAXITREACHED_FORCESNLPsolver_final (0)
 #define TIMEOUT_FORCESNLPsolver_final (2)

@@ -35,6 +35,8 @@
 #ifndef NMPC_B200_H
 #define NMPC_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -133,6 +135,44 @@ int nmpc_solve_batch_host_mixed_f64(int B, int N, int mcap, const double *xinit,
                                     const double *hdr, const double *rows, const int *nrows, int variant,
                                     const nmpc_opts *opts, double *z_out, int *info_int, double *info_real);
 
+/* ---- multi-GPU: one process per GPU, contiguous sharding, end-of-batch NCCL all-gather -----------
+ * The NMPC instances are independent (single-vehicle planner): the solve needs no collective.  The only exchange is
+ * the collation of the results, and it costs no copy: every rank's kernel writes its z straight into its slice of ONE
+ * buffer of world * B_local problems, and an in-place ncclAllGather (sendbuff = recvbuff + rank * count) on the same
+ * stream completes the other slices.  Allocate that buffer with nmpc_comm_alloc (ncclMemAlloc + ncclCommRegister:
+ * NCCL then works on the user buffer itself, NVLS-eligible) or pass any device buffer.
+ *   nmpc_comm_unique_id   rank 0 makes the 128-byte id; the host application distributes it (MPI, a file, torchrun's
+ *                         store ... -- plumbing, not part of this library)
+ *   nmpc_comm_create      collective over all ranks; the CUDA device of the calling thread is the rank's GPU
+ *   nmpc_comm_wrap        adopt an ncclComm_t the application already has (same libnccl)
+ *   nmpc_solve_batch_sharded_f64 / _f32
+ *                         local shard in (B_local problems, layouts as nmpc_solve_batch_f64 / _f32; every rank the same
+ *                         B_local, even), z_all [world * B_local][N][17] and info_int_all [world * B_local][4] out on
+ *                         every rank, info_real_local [B_local][8] for the own shard; mixed != 0 (f64) selects the
+ *                         mixed-precision kernel; _f32 always uses it
+ *   nmpc_collate_inplace  the bare in-place all-gather of any buffer of world * bytes_per_rank bytes
+ * libnccl.so.2 is resolved at run time (the copy already loaded in the process, else the system's; $NMPC_B200_NCCL
+ * overrides), so single-GPU users carry no NCCL dependency.                                                   */
+typedef struct nmpc_comm nmpc_comm;
+int nmpc_comm_unique_id(char id[128]);
+int nmpc_comm_create(int world, int rank, const char id[128], nmpc_comm **comm);
+int nmpc_comm_wrap(void *nccl_comm, int world, int rank, nmpc_comm **comm);
+int nmpc_comm_destroy(nmpc_comm *comm);
+int nmpc_comm_rank(const nmpc_comm *comm);
+int nmpc_comm_world(const nmpc_comm *comm);
+int nmpc_comm_nccl_version(void);
+int nmpc_comm_alloc(nmpc_comm *comm, size_t bytes, void **ptr);
+int nmpc_comm_free(nmpc_comm *comm, void *ptr);
+int nmpc_solve_batch_sharded_f64(nmpc_comm *comm, int B_local, int N, int mcap, const double *xinit,
+                                 const double *z0, const double *hdr, const double *rows, const int *nrows,
+                                 int variant, const nmpc_opts *opts, double *z_all, int *info_int_all,
+                                 double *info_real_local, int mixed, void *cuda_stream);
+int nmpc_solve_batch_sharded_f32(nmpc_comm *comm, int B_local, int N, int mcap, const float *xinit,
+                                 const float *z0, const float *hdr, const float *rows, const int *nrows,
+                                 int variant, const nmpc_opts *opts, float *z_all, int *info_int_all,
+                                 float *info_real_local, void *cuda_stream);
+int nmpc_collate_inplace(nmpc_comm *comm, void *buf_all, size_t bytes_per_rank, void *cuda_stream);
+
 /* ---- stand-alone structured KKT factorisation / backsolve (device pointers) ------------------
  * The split the reference binary makes internally (f_17_PD_ldlchol_rowmajor ... vs
  * f_17_ldl_forward_solve_rm / f_13_backward_solve_rm) for the Riccati factor:
@@ -172,6 +212,22 @@ int nmpc_shift_warm_start_f64(int B, int N, const double *z_prev, double *xinit,
 /* NMPCSolver::updateFORCESResults' yaw wrap (nmpc_solver.cpp:531-541) on an adopted plan z [B][N][17], in place:
  * yaw < -PI -> yaw + 2 PI, yaw > PI -> yaw - 2 PI, with the reference's PI = 3.1415926 (:3).               */
 int nmpc_wrap_yaw_f64(int B, int N, double *z, void *cuda_stream);
+
+/* ---- result handling of a replan, device-resident (NMPCSolver::solveNMPC, nmpc_solver.cpp:398-427, 363-364) ----
+ * z_prev [B][N][17] is the plan in force (mpc_output_).  An agent whose new solve is accepted -- info_int[b][0] == 1, or
+ * accept[b] != 0 when the caller supplies its own mask (the reference also tolerates exit flag 0 after more than three
+ * replans: host policy, host/forces_wrappers.hpp::SolveAcceptance) -- adopts z_new (yaw wrapped into (-PI, PI] when
+ * wrap_yaw != 0, updateFORCESResults :531-541).  A rejected agent takes nothing from the failed solve (its output may
+ * be NaN): its plan becomes the cold guess of initMPCOutput (:265-286) at its current state -- odom[b] (9 doubles) when
+ * given, else stage 2 of the old plan (where that plan puts the vehicle at the next cycle) -- so that the next shift
+ * + solve is a cold start, as in the reference.  cold [B] (may be NULL) receives 1 for the rejected agents.
+ * accept, odom may be NULL; info_int may be NULL only if accept is given.                                   */
+int nmpc_adopt_plans_f64(int B, int N, const double *z_new, const int *info_int, const int *accept,
+                         const double *odom, double *z_prev, int *cold, int wrap_yaw, void *cuda_stream);
+/* order [B] <- agent indices sorted by the previous solve's iteration count, longest first (failed agents, which
+ * restart cold, first; ties by index): the launch order for nmpc_solve_batch_ordered_f64 in a receding-horizon
+ * stream.  One CTA, rank by counting out of shared memory; B <= 12288.                                      */
+int nmpc_rank_longest_first(int B, const int *info_int, int *order, void *cuda_stream);
 
 /* ---- reference sampling + yaw reference, device-resident ---------------
  * Batched NMPCSolver::getCurTraj (plan_manage/src/nmpc_solver.cpp:109-142) + calculate_yaw

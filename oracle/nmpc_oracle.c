@@ -33,6 +33,7 @@
 #include <tgmath.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -443,7 +444,8 @@ int nmpc_oracle_kkt_solve(int N, const double *Phi, const double *g, const doubl
 
 /* ------------------------------------------------ mixed precision: single-precision Riccati ---- */
 /*
- * opts.mixed = 1 (the CUDA product's *_mixed / *_f32 entry points): the Newton system is written in
+ * opts.mixed = 1 (the CUDA product's *_mixed / *_f32 entry points; 2 = the same in double precision, i.e. the
+ * fp64 product's own Riccati algorithm on the CPU): the Newton system is written in
  * DELTA form -- the right-hand side is the full KKT residual, evaluated in double precision at the
  * current (z, y), so the unknowns are (dz, dy) -- and solved by a Riccati recursion over
  * xi = [x(9); u_prev(4)] carried out entirely in SINGLE precision.  The iterate, the residuals, the
@@ -452,123 +454,20 @@ int nmpc_oracle_kkt_solve(int N, const double *Phi, const double *g, const doubl
  * Dense restatement of what csrc/nmpc_ipm_mixed.cuh does with the structured Jacobian.
  *   min 1/2 dz'Phi dz + g'dz  s.t.  E dz_{k+1} = C_k dz_k + d_k,  dz_0[8:17] = 0;   dy = QP multipliers
  */
-typedef float sreal;
-static int chol4_s(sreal A[4][4])
-{
-    for (int j = 0; j < 4; j++) {
-        sreal dd = A[j][j];
-        for (int k = 0; k < j; k++) dd -= A[j][k] * A[j][k];
-        if (!(dd > 0)) return -5;
-        dd = sqrtf(dd);
-        A[j][j] = dd;
-        for (int i = j + 1; i < 4; i++) {
-            sreal t = A[i][j];
-            for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
-            A[i][j] = t / dd;
-        }
-    }
-    return 0;
-}
-static void fsub4_s(sreal L[4][4], sreal *x)
-{
-    for (int i = 0; i < 4; i++) { sreal t = x[i]; for (int k = 0; k < i; k++) t -= L[i][k] * x[k]; x[i] = t / L[i][i]; }
-}
-static void bsub4_s(sreal L[4][4], sreal *x)
-{
-    for (int i = 3; i >= 0; i--) { sreal t = x[i]; for (int k = i + 1; k < 4; k++) t -= L[k][i] * x[k]; x[i] = t / L[i][i]; }
-}
-static int riccati_solve_single(int N, real (*Phi)[NZ][NZ], real (*g)[NZ], real (*C)[NXI][NZ], real (*d)[NXI],
-                                real (*dz)[NZ], real (*dy)[NXI])
-{
-    static _Thread_local sreal K[NS_MAX][4][NXI], kff[NS_MAX][4], J[NS_MAX][NXI][NZ], Ph[NS_MAX][NZ][NZ], gs[NS_MAX][NZ], ds[NS_MAX][NXI];
-    sreal P[NXI][NXI], p[NXI];
-    for (int k = 0; k < N; k++) {
-        for (int i = 0; i < NZ; i++) { gs[k][i] = (sreal)g[k][i]; for (int j = 0; j < NZ; j++) Ph[k][i][j] = (sreal)Phi[k][i][j]; }
-        if (k < N - 1) for (int r = 0; r < NXI; r++) { ds[k][r] = (sreal)d[k][r]; for (int j = 0; j < NZ; j++) J[k][r][j] = (sreal)C[k][r][j]; }
-    }
-    for (int k = N - 1; k >= 0; k--) {
-        sreal Q[NZ][NZ], q[NZ];
-        for (int i = 0; i < NZ; i++) { q[i] = gs[k][i]; for (int j = 0; j < NZ; j++) Q[i][j] = Ph[k][i][j]; }
-        if (k < N - 1) {
-            sreal PJ[NXI][NZ], t[NXI];
-            for (int i = 0; i < NXI; i++) {
-                sreal a = p[i];
-                for (int r = 0; r < NXI; r++) a += P[i][r] * ds[k][r];
-                t[i] = a;
-                for (int j = 0; j < NZ; j++) { sreal b = 0; for (int r = 0; r < NXI; r++) b += P[i][r] * J[k][r][j]; PJ[i][j] = b; }
-            }
-            for (int i = 0; i < NZ; i++) {
-                sreal a = 0;
-                for (int r = 0; r < NXI; r++) a += J[k][r][i] * t[r];
-                q[i] += a;
-                for (int j = 0; j < NZ; j++) { sreal b = 0; for (int r = 0; r < NXI; r++) b += J[k][r][i] * PJ[r][j]; Q[i][j] += b; }
-            }
-        }
-        sreal L[4][4], Y[4][NXI], y0[4];
-        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) L[i][j] = Q[i][j];
-        if (chol4_s(L)) return -5;
-        for (int c = 0; c < NXI; c++) {
-            sreal x[4];
-            for (int r = 0; r < 4; r++) x[r] = Q[r][e_col(c)];
-            fsub4_s(L, x);
-            for (int r = 0; r < 4; r++) Y[r][c] = x[r];
-            bsub4_s(L, x);
-            for (int r = 0; r < 4; r++) K[k][r][c] = -x[r];
-        }
-        for (int r = 0; r < 4; r++) y0[r] = q[r];
-        fsub4_s(L, y0);
-        { sreal x[4]; for (int r = 0; r < 4; r++) x[r] = y0[r]; bsub4_s(L, x); for (int r = 0; r < 4; r++) kff[k][r] = -x[r]; }
-        for (int i = 0; i < NXI; i++) {
-            sreal a = q[e_col(i)];
-            for (int r = 0; r < 4; r++) a -= Y[r][i] * y0[r];
-            p[i] = a;
-            for (int j = 0; j < NXI; j++) {
-                sreal b = Q[e_col(i)][e_col(j)];
-                for (int r = 0; r < 4; r++) b -= Y[r][i] * Y[r][j];
-                P[i][j] = b;
-            }
-        }
-    }
-    /* stage 0: states fixed, u_prev free */
-    sreal dxi[NXI];
-    {
-        sreal L[4][4], x[4];
-        for (int i = 0; i < 4; i++) { x[i] = -p[9 + i]; for (int j = 0; j < 4; j++) L[i][j] = P[9 + i][9 + j]; }
-        if (chol4_s(L)) return -5;
-        fsub4_s(L, x); bsub4_s(L, x);
-        for (int i = 0; i < 9; i++) dxi[i] = 0;
-        for (int i = 0; i < 4; i++) dxi[9 + i] = x[i];
-    }
-    static _Thread_local sreal dzs[NS_MAX][NZ];
-    for (int k = 0; k < N; k++) {
-        for (int r = 0; r < 4; r++) {
-            sreal a = kff[k][r];
-            for (int c = 0; c < NXI; c++) a += K[k][r][c] * dxi[c];
-            dzs[k][r] = a;
-        }
-        for (int i = 0; i < NXI; i++) dzs[k][e_col(i)] = dxi[i];
-        if (k < N - 1)
-            for (int r = 0; r < NXI; r++) {
-                sreal a = ds[k][r];
-                for (int j = 0; j < NZ; j++) a += J[k][r][j] * dzs[k][j];
-                dxi[r] = a;
-            }
-    }
-    sreal yn[NXI];
-    for (int i = 0; i < NXI; i++) { yn[i] = 0; dy[0][i] = 0; }
-    for (int k = N - 1; k >= 1; k--) {
-        sreal v[NZ];
-        for (int i = 0; i < NZ; i++) {
-            sreal a = gs[k][i];
-            for (int j = 0; j < NZ; j++) a += Ph[k][i][j] * dzs[k][j];
-            if (k < N - 1) for (int r = 0; r < NXI; r++) a += J[k][r][i] * yn[r];
-            v[i] = a;
-        }
-        for (int i = 0; i < NXI; i++) { yn[i] = v[e_col(i)]; dy[k][i] = (real)yn[i]; }
-    }
-    for (int k = 0; k < N; k++) for (int i = 0; i < NZ; i++) dz[k][i] = (real)dzs[k][i];
-    return 0;
-}
+#define sreal float
+#define RIC_NAME(x) x##_s
+#define RIC_SQRT sqrtf
+#include "riccati_dense.inc"
+#undef sreal
+#undef RIC_NAME
+#undef RIC_SQRT
+#define sreal double
+#define RIC_NAME(x) x##_d
+#define RIC_SQRT sqrt
+#include "riccati_dense.inc"
+#undef sreal
+#undef RIC_NAME
+#undef RIC_SQRT
 
 /* ------------------------------------------------------------------ IPM ------------------ */
 
@@ -753,7 +652,7 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
             }
         }
         if (o->mixed) {
-            if (riccati_solve_single(N, w->Phi, w->gt, w->Cm, e->d, w->dz, w->yn)) { flag = -5; break; }
+            if ((o->mixed == 2 ? riccati_solve_d : riccati_solve_s)(N, w->Phi, w->gt, w->Cm, e->d, w->dz, w->yn)) { flag = -5; break; }
             for (int k = 0; k < N; k++) for (int i = 0; i < NXI; i++) w->yn[k][i] += w->y[k][i];   /* y + dy */
         } else if (kkt_solve(N, w->Phi, w->gt, w->Cm, e->d, w->dz, w->yn)) { flag = -5; break; }
         if (flag != 0) break;
@@ -914,5 +813,31 @@ int nmpc_oracle_solve_batch_ex(int B, int N, int mcap, const real *xinit, const 
         }
         free(w);
     }
+    return 0;
+}
+
+/* One thread, one problem after the other, each solve timed on its own (CLOCK_MONOTONIC): how the planner runs the
+ * reference solver (num_of_threads = 1, plan_manage/src/forces_normal.cpp:31).  seconds [B]. */
+int nmpc_oracle_solve_batch_timed(int B, int N, int mcap, const real *xinit, const real *z0, const real *hdr,
+                                  const real *rows, const int *nrows, int variant, const nmpc_oracle_opts *opts,
+                                  real *z_out, int *info_int, real *info_real, double *seconds)
+{
+    if (N < 2 || N > NS_MAX || mcap < 0 || mcap > MC_MAX || !seconds) return -11;
+    nmpc_oracle_opts o;
+    if (opts) o = *opts; else nmpc_oracle_default_opts(&o);
+    work_t *w = (work_t *)malloc(sizeof(work_t));
+    for (int b = 0; b < B; b++) {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        w->N = N; w->mcap = mcap; w->variant = variant;
+        w->hdr = hdr + (size_t)b * N * 10;
+        w->rows = rows + (size_t)b * N * mcap * 4;
+        w->nrows = nrows + (size_t)b * N;
+        solve_one(w, &o, xinit + (size_t)b * 9, z0 + (size_t)b * N * NZ, z_out + (size_t)b * N * NZ,
+                  info_int + (size_t)b * 4, info_real + (size_t)b * 8, 0, 0, 0, 0);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        seconds[b] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
+    free(w);
     return 0;
 }

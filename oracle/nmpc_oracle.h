@@ -43,7 +43,8 @@ typedef struct {
     int max_bt;        /* backtracking steps per iteration                            */
     int pc;            /* 1: Mehrotra predictor-corrector (affine solve -> sigma, corrector rhs)  */
     int mixed;         /* 1: delta-form Newton system solved by a SINGLE-precision Riccati recursion, everything
-                          else (iterate, residuals, step rule, line search) in `real`; see nmpc_oracle.c  */
+                          else (iterate, residuals, step rule, line search) in `real`; 2: the same recursion in double
+                          precision (the product's own factorisation on the CPU); 0: Schur complement + refinement  */
 } nmpc_oracle_opts;
 
 void nmpc_oracle_default_opts(nmpc_oracle_opts *o);
@@ -70,6 +71,13 @@ int nmpc_oracle_solve_batch_ex(int B, int N, int mcap, const real *xinit, const 
                                const nmpc_oracle_opts *opts, real *z_out, int *info_int,
                                real *info_real, real *y_out, real *zl_out, real *zu_out,
                                real *lc_out, int nthreads);
+
+/* single thread, problem after problem, every solve timed on its own (how the planner runs the reference solver:
+ * num_of_threads = 1, forces_normal.cpp:31); seconds [B] */
+int nmpc_oracle_solve_batch_timed(int B, int N, int mcap, const real *xinit, const real *z0,
+                                  const real *hdr, const real *rows, const int *nrows, int variant,
+                                  const nmpc_oracle_opts *opts, real *z_out, int *info_int,
+                                  real *info_real, double *seconds);
 
 /* One structured KKT solve (ForcesPro-style Schur complement, dense 17/13 blocks):
  *   min 1/2 dz' Phi dz + g' dz   s.t.  E dz_{k+1} = C_k dz_k + d_k ,  dz_0[8:17] = 0

@@ -92,6 +92,22 @@ def solve_batch(batch, dtype=np.float64, opts: OracleOpts | None = None, nthread
     return out
 
 
+def solve_batch_timed(batch, opts: OracleOpts | None = None):
+    """One thread, every solve timed on its own.  Returns dict(z, flag, it, seconds [B])."""
+    lib = _lib(np.float64)
+    B, N, mcap = batch.B, batch.N, batch.mcap
+    a = lambda x, dt=np.float64: np.ascontiguousarray(x, dt)
+    xinit, z0, hdr, rows, nrows = a(batch.xinit), a(batch.z0), a(batch.hdr), a(batch.rows), a(batch.nrows, np.int32)
+    z = np.zeros((B, N, 17)); ii = np.zeros((B, 4), np.int32); ir = np.zeros((B, 8)); sec = np.zeros(B)
+    o = opts or default_opts()
+    lib.nmpc_oracle_solve_batch_timed.restype = ctypes.c_int
+    rc = lib.nmpc_oracle_solve_batch_timed(B, N, mcap, _p(xinit), _p(z0), _p(hdr), _p(rows), _p(nrows), int(batch.variant),
+                                           ctypes.byref(o), _p(z), _p(ii), _p(ir), _p(sec))
+    if rc != 0:
+        raise ValueError(f"nmpc_oracle_solve_batch_timed rejected the arguments (rc={rc})")
+    return dict(z=z, flag=ii[:, 0].copy(), it=ii[:, 1].copy(), seconds=sec)
+
+
 def model_eval(z, p130, stage, n_stages=20, variant=0):
     """Mirror of the reference casadi2forces callback for one stage (always fp64)."""
     lib = _lib(np.float64)

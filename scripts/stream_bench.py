@@ -51,7 +51,7 @@ for step in range(a.replans):
         _ = gcmd[:, 4].cpu()
     lat.append(time.perf_counter() - t0)
     its.append(it.mean()); fails += int((flag != 1).sum())
-    resets += s.reset_failed(flag)
+    resets += int((flag != 1).sum())      # failed agents restart cold next cycle (nmpc_adopt_plans_f64, inside the replan)
 lat = np.array(lat[WARM:]) * 1e3
 if world > 1:
     t = torch.from_numpy(lat).to(dev)

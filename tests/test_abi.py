@@ -81,8 +81,50 @@ def test_no_cpu_fallback_without_a_device(cuda_lib):
         assert "rc=-101" in str(e)
     else:
         raise AssertionError("solve_host computed something without a GPU")
+    # the reference-named symbols answer in the reference's own vocabulary (header :110-139): "no CUDA device" becomes
+    # LICENSE_ERROR (-100, "solver not valid on this machine"), which the planner treats like any failed solve
     w = forces.FORCESNormal()
-    assert w.solve_params() == -101
+    assert w.solve_params() == -100
+
+
+def _build_dropin_probe(tmp_path):
+    """The drop-in tree (same directory / header / archive names as plan_manage/solver/) and a planner-side translation
+    unit that uses only the reference's header names, macros and symbols, linked with the reference's own link line
+    (plan_manage/CMakeLists.txt:58-65 include + link directories, :82-83 `libFORCESNLPsolver_normal.a
+    libFORCESNLPsolver_final.a` by file name) -- no cudart, no extra library."""
+    host = os.path.join(ROOT, "forces_resilient_planner_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s", "dropin"])
+    d = os.path.join(ROOT, "build", "dropin", "solver")
+    exe = str(tmp_path / "dropin_tu")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-o", exe, os.path.join(ROOT, "tests", "tools", "dropin_tu.cpp"),
+                           "-I", f"{d}/normal/FORCESNLPsolver_normal/include", "-I", f"{d}/final/FORCESNLPsolver_final/include",
+                           "-L", f"{d}/normal/FORCESNLPsolver_normal/lib", "-L", f"{d}/final/FORCESNLPsolver_final/lib",
+                           "-l:libFORCESNLPsolver_normal.a", "-l:libFORCESNLPsolver_final.a"])
+    return exe
+
+
+def test_dropin_archives_link_with_the_reference_link_line(cuda_lib, tmp_path):
+    import torch
+    exe = _build_dropin_probe(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "exitflags 1 1 maxit 200" in out.stdout, out.stdout + out.stderr
+    else:       # no device: both calls answer LICENSE_ERROR and say why; nothing is computed on the CPU
+        assert out.returncode == 100 and "exitflags -100 -100" in out.stdout, out.stdout + out.stderr
+        assert "exitflag -100" in out.stdout and "cuda" in out.stdout.lower()
+    # a library that cannot be found is the same failure, reported by the stub itself
+    env = dict(os.environ, NMPC_B200_LIB="/nonexistent/libnmpc_b200.so")
+    host = os.path.join(ROOT, "forces_resilient_planner_b200", "host")
+    exe2 = str(tmp_path / "stub_only")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-o", exe2, "-x", "c", "-", "-I", os.path.join(ROOT, "include"),
+                    "-DNMPC_STUB_VARIANT=normal", '-DNMPC_STUB_HEADER="FORCESNLPsolver_normal.h"',
+                    os.path.join(host, "forces_stub.c")], check=True, input=b"""
+#include "FORCESNLPsolver_normal.h"
+int main(void){ static FORCESNLPsolver_normal_params p; static FORCESNLPsolver_normal_output o; static FORCESNLPsolver_normal_info i;
+  return FORCESNLPsolver_normal_solve(&p, &o, &i, 0, 0) == LICENSE_ERROR_FORCESNLPsolver_normal ? 0 : 1; }""")
+    # without a default path and with a bad NMPC_B200_LIB the loader's search path is the last resort: not found here
+    out = subprocess.run([exe2], capture_output=True, text=True, env=dict(env, LD_LIBRARY_PATH=""))
+    assert out.returncode == 0 and "cannot load libnmpc_b200.so" in out.stderr
 
 
 def test_product_never_touches_the_oracle():

@@ -313,6 +313,55 @@ def test_receding_horizon_stream_matches_cpu_closed_loop():
     assert s.graph is not None
 
 
+def test_failed_agent_leaves_nothing_behind_and_restarts_cold():
+    """Result handling of solveNMPC (nmpc_solver.cpp:398-427, 363-364), per agent: a failed solve (here: NaN
+    references for one agent during one cycle -> NaN output, exit -6) is not adopted; that agent restarts from the
+    cold guess at its state on the next cycle, the others are untouched -- same commands as a fleet without the fault."""
+    from forces_resilient_planner_b200 import stream as ST
+    b = W.config2(24)
+    runs = []
+    for inject in (False, True):
+        rng = np.random.Generator(np.random.PCG64(5))
+        s = ST.RecedingHorizonStream(b, use_graph=True)
+        ext = b.hdr[:, 0, 3:6].copy()
+        hist = []
+        for step in range(8):
+            ref, yaw, ext = ST.synthetic_refs(b, step, rng, ext)
+            if inject and step == 4:
+                ref = ref.copy(); ref[3] = np.nan
+            cmd, flag, it = s.replan(ref, yaw, ext)
+            hist.append((cmd.copy(), flag.copy(), it.copy()))
+            if inject and step == 4:
+                assert flag[3] in (-6, -7) and np.all(np.delete(flag, 3) == 1)
+                assert not np.all(np.isfinite(s.z[3].cpu().numpy()))           # the failed output really is garbage ...
+            if inject and step == 5:
+                zp = s.zprev.cpu().numpy()
+                assert np.all(np.isfinite(zp))                                 # ... and never entered the plan in force
+                assert flag[3] == 1 and it[3] > hist[3][2][3]                  # cold restart: more iterations than a warm one
+        runs.append(hist)
+    clean, faulty = runs
+    for step in range(8):
+        keep = np.arange(b.B) != 3
+        assert np.array_equal(clean[step][1][keep], faulty[step][1][keep])
+        assert np.max(np.abs(clean[step][0][keep] - faulty[step][0][keep])) == 0.0, step
+    assert np.all(faulty[7][1] == 1) and np.all(np.isfinite(faulty[7][0]))
+    # the restarted agent is back on the fleet's track two cycles later (same problem, different start of the iteration)
+    assert np.max(np.abs(clean[7][0][3] - faulty[7][0][3])) < 0.5
+
+
+def test_rank_longest_first_equals_stable_argsort():
+    import torch
+    from forces_resilient_planner_b200 import prep
+    rng = np.random.default_rng(2)
+    for B in (1, 37, 1024, 5000):
+        ii = np.zeros((B, 4), np.int32)
+        ii[:, 0] = rng.choice([1, 1, 1, 1, 0, -5, -7], B); ii[:, 1] = rng.integers(3, 30, B)
+        key = ii[:, 1] + 1000 * (ii[:, 0] != 1)
+        want = np.argsort(-key, kind="stable").astype(np.int32)
+        got = prep.rank_longest_first(torch.from_numpy(ii).cuda(), torch.empty(B, dtype=torch.int32, device="cuda")).cpu().numpy()
+        assert np.array_equal(got, want), B
+
+
 def test_stream_with_propagated_ellipsoids_matches_cpu_closed_loop():
     """The same loop with the corridor tightened by the disturbance ellipsoids propagated along the
     previous plan on the device, against the literal CPU restatement."""

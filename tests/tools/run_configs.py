@@ -3,7 +3,7 @@ Full-size runs of BASELINE configs 3 and 4 (parity-test configs, not the bench l
 
   python tests/tools/run_configs.py --config 3                       # 1 GPU: B = 65536, N = 20, 4-10 rows
   torchrun --nproc-per-node 8 ... tests/tools/run_configs.py --config 4   # 8 GPUs: B = 262144, N = 40, wind sweep,
-                                                                       # NCCL all-gather of the results
+                                                                       # solve + in-place NCCL all-gather (C ABI)
 
 Each prints one JSON line: solves/s (CUDA events around the fused launch), converged fraction,
 iteration statistics, for the fp64 kernel and for the mixed-precision kernel (float arrays), both at the reference tolerances,
@@ -59,52 +59,71 @@ def config3():
 
 
 def config4():
+    """BASELINE config 4: 262144 problems (512 x 512 wind sweep), N = 40, sharded over the GPUs of the box; solve +
+    end-of-batch collation through the C ABI's own NCCL path (nmpc_solve_batch_sharded_*: the kernel writes into its
+    slice of one NCCL-registered buffer, in-place ncclAllGather on the same stream)."""
     import torch.distributed as dist
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")                  # plumbing only: the NCCL id travels over it
     side, N = 512, 40
     B = side * side
+    per = D.per_rank(B, world)
     lo, hi = D.shard_range(B, rank, world)
-    # wind sweep of the global index range [lo, hi): |f| = linspace(0,4,side) x azimuth linspace(0,2pi,side)
     idx = np.arange(lo, hi)
     mag = np.linspace(0, 4, side)[idx // side]; az = np.linspace(0, 2 * np.pi, side, endpoint=False)[idx % side]
     fext = np.stack([mag * np.cos(az), mag * np.sin(az), np.zeros(hi - lo)], -1)
     b = W.config2(hi - lo, N, seed=W.SEED + 4 + 1000 * rank, fext=fext)
-    out = {"config": f"config4: B={B} (512x512 wind sweep), N=40, sharded over {world} GPU(s), NCCL all-gather of z"}
-    for name, dt, opts in (("fp64_reference_tolerances", np.float64, _lib.default_opts()),
-                           ("fp64_predictor_corrector", np.float64, _lib.default_opts(pc=1, mu0=10.0)),
-                           ("mixed_f32_reference_tolerances", np.float32, _lib.default_opts())):
-        db, res, ms = timed_solve(b, dt, opts, dev)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([float(np.sum(res.flag == 1)), float(res.it.sum()), float(res.it.max())], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            mx = cnt[2:].clone(); dist.all_reduce(cnt, op=dist.ReduceOp.SUM); dist.all_reduce(mx, op=dist.ReduceOp.MAX); cnt[2] = mx[0]
-        # end-of-batch collation: all ranks get all results (z + flags + iterations)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        if world > 1:
-            gz, gf, gi = D.all_gather_results(db.z, db.info_int[:, 0].contiguous(), db.info_int[:, 1].contiguous(), B)
+    assert b.B == per, "512*512 divides evenly over 1/2/4/8 ranks"
+    col = D.NcclCollator(rank, world, dev) if world > 1 else None
+    out = {"config": f"config4: B={B} (512x512 wind sweep), N=40, sharded over {world} GPU(s), solve + in-place NCCL all-gather of z and info",
+           "nccl_version": int(_lib.load().nmpc_comm_nccl_version()) if world > 1 else None}
+    st = torch.cuda.current_stream(dev)
+    for name, dt, opts, mixed in (("fp64_reference_tolerances", np.float64, _lib.default_opts(), False),
+                                  ("fp64_predictor_corrector", np.float64, _lib.default_opts(pc=1, mu0=10.0), False),
+                                  ("mixed_f32_reference_tolerances", np.float32, _lib.default_opts(), True)):
+        db = S.DeviceBatch(b, dt, dev)
+        t_dt = torch.float64 if dt == np.float64 else torch.float32
+        if col:
+            z_all = col.alloc((world * per, N, 17), t_dt); ii_all = col.alloc((world * per, 4), torch.int32)
+            run = lambda: col.solve_sharded(db, z_all, ii_all, opts, mixed=mixed)
         else:
-            gz, gf, gi = db.z, db.info_int[:, 0], db.info_int[:, 1]
-        torch.cuda.synchronize(dev)
-        gather_ms = (time.perf_counter() - t0) * 1e3
-        # checksum of checksums: sum over the gathered tensor == all-reduced sum of the local shards
-        local_sum = db.z.double().sum().reshape(1)
+            z_all, ii_all = db.z, db.info_int
+            run = lambda: S.solve_device(db, opts, mixed=mixed)
+        run(); torch.cuda.synchronize(dev)                      # warm-up (also NCCL's first-collective set-up)
+        ms_all, ms_solve = [], []
+        for rep in range(3):
+            if world > 1:
+                dist.barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(st); run(); e1.record(st); torch.cuda.synchronize(dev)
+            ms_all.append(e0.elapsed_time(e1))
+            e0.record(st); S.solve_device(db, opts, mixed=mixed); e2.record(st); torch.cuda.synchronize(dev)   # the solve alone, for the split
+            ms_solve.append(e0.elapsed_time(e2))
+        t = torch.tensor([min(ms_all), min(ms_solve)], dtype=torch.float64)
+        mine = ii_all[rank * per:(rank + 1) * per].cpu().numpy() if col else ii_all.cpu().numpy()
+        cnt = torch.tensor([float(np.sum(mine[:, 0] == 1)), float(mine[:, 1].sum()), float(mine[:, 3].sum())], dtype=torch.float64)
+        mx = torch.tensor([float(mine[:, 1].max())], dtype=torch.float64)
+        # checksum of checksums: the gathered buffer on every rank sums to the sum of the shards' own sums
+        local_sum = (z_all[rank * per:(rank + 1) * per] if col else z_all).double().sum().cpu().reshape(1)
+        full_sum = z_all.double().sum().cpu().reshape(1)
+        flags_all = ii_all[:, 0].cpu().numpy()
         if world > 1:
-            dist.all_reduce(local_sum, op=dist.ReduceOp.SUM)
-        full_sum = gz.double().sum()
-        ok = bool(torch.isclose(full_sum, local_sum[0], rtol=1e-9, atol=1e-3)) and gz.shape[0] == B
-        out[name] = dict(solves_per_sec=B / (float(t.item()) * 1e-3), ms=float(t.item()), converged_frac=float(cnt[0].item()) / B,
-                         mean_it=float(cnt[1].item()) / B, max_it=int(cnt[2].item()), allgather_ms=gather_ms,
-                         allgather_bytes=int(gz.numel() * gz.element_size()), checksum_of_checksums_ok=ok)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(local_sum, op=dist.ReduceOp.SUM)
+        ok = bool(torch.isclose(full_sum, local_sum, rtol=1e-9, atol=1e-3)) and z_all.shape[0] == B
+        out[name] = dict(solves_per_sec=B / (float(t[0]) * 1e-3), ms_solve_plus_collation=float(t[0]), ms_solve_only=float(t[1]),
+                         collation_bytes=int(z_all.numel() * z_all.element_size() + ii_all.numel() * 4),
+                         converged_frac=float(cnt[0]) / B, converged_frac_seen_in_gathered_flags=float(np.mean(flags_all == 1)),
+                         mean_it=float(cnt[1]) / B, max_it=int(mx[0]), resolved_in_fp64_frac=float(cnt[2]) / B,
+                         checksum_of_checksums_ok=ok)
+        del z_all, ii_all
     if rank == 0:
         print(json.dumps(out), flush=True)
+    if col:
+        col.close()
     if world > 1:
         dist.destroy_process_group()
 
