@@ -1094,7 +1094,23 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     T f_cur, th_cur, ls_cur;
     s.evaluate(T(0), f_cur, th_cur, ls_cur);
     __syncwarp();
-    for (it = 0;; it++) {
+    // The stage-0 states are fixed by the xinit equality: their bounds and the stage-0 corridor rows are not part of the
+    // barrier problem.  If xinit violates one of them beyond TolIneq, the reference's NLP -- which carries them
+    // (mpc_generator_normal.m:29-50) -- has no feasible point: NOPROGRESS (-7), zero iterations, violation in res_ineq.
+    bool infeasible0;
+    {
+        T v0 = T(0);
+        if (lane >= 8 && lane < NZ) v0 = fmax(lower_bound<T>(lane) - s.Z[lane], s.Z[lane] - upper_bound<T>(lane));
+        const int m0 = min(nr[0], mcap);
+        for (int j = lane; j < m0; j += 32) {
+            T r[4]; s.load_row(0, j, r);
+            v0 = fmax(v0, r[0] * s.Z[8] + r[1] * s.Z[9] + r[2] * s.Z[10] - (r[3] + C::hu));
+        }
+        v0 = warp_max(v0);
+        infeasible0 = v0 > (T)o.tol_ineq;
+        if (infeasible0) { flag = -7; rin_n = v0; }
+    }
+    for (it = 0; !infeasible0; it++) {
         T csum, cmin;
         s.residuals(rs_n, req_n, rin_n, rcomp, csum, cmin);
         mu = csum / (T)ncomp;

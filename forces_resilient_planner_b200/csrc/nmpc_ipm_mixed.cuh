@@ -465,7 +465,22 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
     s.evaluate(0.0, f_cur, th_cur, ls_cur, req_n, rs_n);
     __syncwarp();
     const int it_cap = min(o.maxit, MIXED_BAIL_IT);
-    for (it = 0;; it++) {
+    // xinit outside a stage-0 bound or stage-0 corridor row (beyond TolIneq): the reference's NLP is infeasible -> NOPROGRESS (-7),
+    // zero iterations, the violation in res_ineq (see nmpc_ipm.cuh)
+    bool infeasible0;
+    {
+        double v0 = 0.0;
+        if (lane >= 8 && lane < NZ) v0 = fmax(lower_bound<double>(lane) - s.Z[lane], s.Z[lane] - upper_bound<double>(lane));
+        const int m0 = min(nr[0], mcap);
+        for (int j = lane; j < m0; j += 32) {
+            double r[4]; s.load_row(0, j, r);
+            v0 = fmax(v0, r[0] * s.Z[8] + r[1] * s.Z[9] + r[2] * s.Z[10] - (r[3] + C::hu));
+        }
+        v0 = warp_max(v0);
+        infeasible0 = v0 > o.tol_ineq;
+        if (infeasible0) { flag = -7; rin_n = v0; }
+    }
+    for (it = 0; !infeasible0; it++) {
         double csum, cmin;
         s.residuals(rin_n, rcomp, csum, cmin);
         mu = csum / (double)ncomp;

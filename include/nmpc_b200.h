@@ -25,6 +25,17 @@
  *        info_real [B][8]       -> res_eq, res_ineq, rsnorm, rcompnorm, pobj, mu, alpha_p, alpha_d
  *                                  (the fields of FORCESNLPsolver_normal_info, header :241-301)
  *
+ *      exit flags (info_int[b][0]; reference vocabulary, header :110-139):
+ *         1  OPTIMAL        all four inf-norms <= tolerance (mpc_generator_normal.m:76-79)
+ *         0  MAXITREACHED   opts.maxit iterations without meeting them
+ *        -5  FACTORIZATION  non-positive pivot in the KKT factorisation
+ *        -6  BADFUNCEVAL    NaN / Inf at the first evaluation (bad input)
+ *        -7  NOPROGRESS     NaN / Inf later on, OR the problem has no feasible point because xinit itself violates a
+ *                           stage-0 bound or stage-0 corridor row by more than tol_ineq: the stage-0 states are fixed by
+ *                           the xinit equality (header :156, mpc_generator_normal.m:50), so no iteration can repair that;
+ *                           returned after zero iterations with the violation in info_real[b][1] (res_ineq).
+ *      (A feasible xinit makes the stage-0 bounds and rows redundant; they are then not carried as barrier terms.)
+ *
  *      variant 0 = "normal" stage/terminal costs, 1 = "final" (terminal velocity cost,
  *      matlab_code/mpc/final/mpc_objectiveN_final.m:26).
  *

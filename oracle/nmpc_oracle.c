@@ -565,7 +565,22 @@ static int solve_one(work_t *w, const nmpc_oracle_opts *o, const real *xinit, co
     int cur = 0, flag = 0, it = 0, nbt_total = 0;
     real alpha_p = 0, alpha_d = 0, rs_n = 0, req_n = 0, rin_n = 0, rcomp = 0, mu = 0;
     evaluate(w, w->z, w->s, &w->ev[cur]);
-    for (it = 0;; it++) {
+    /* The stage-0 states are fixed by the xinit equality, so their bounds and the stage-0 corridor rows are not part of
+     * the barrier problem.  If xinit VIOLATES one of them (beyond TolIneq) the reference's NLP -- which does carry
+     * them (mpc_generator_normal.m:29-50) -- has no feasible point; say so in the reference's vocabulary:
+     * NOPROGRESS (-7, header :128), zero iterations, the violation in res_ineq. */
+    real v0 = 0;
+    for (int i = 8; i < NZ; i++) v0 = fmax(v0, fmax(w->lb[i] - w->z[0][i], w->z[0][i] - w->ub[i]));
+    {
+        int m0 = w->nrows[0] < w->mcap ? w->nrows[0] : w->mcap;
+        for (int j = 0; j < m0; j++) {
+            const real *a = row(w, 0, j);
+            v0 = fmax(v0, a[0] * w->z[0][8] + a[1] * w->z[0][9] + a[2] * w->z[0][10] - (a[3] + HU));
+        }
+    }
+    const int infeasible0 = v0 > (real)o->tol_ineq;
+    if (infeasible0) { flag = -7; rin_n = v0; }
+    for (it = 0; !infeasible0; it++) {
         eval_t *e = &w->ev[cur];
         /* ---- residuals */
         rs_n = req_n = rin_n = rcomp = 0;
@@ -840,4 +855,26 @@ int nmpc_oracle_solve_batch_timed(int B, int N, int mcap, const real *xinit, con
     }
     free(w);
     return 0;
+}
+
+/* The restated model behind the reference callback's own signature (FORCESNLPsolver_normal_extfunc): what kkt_check.c is
+ * driven with where oracle/_ref is not available.  normal variant / final variant. */
+static void compat_cb(double *x, double *p, double *f, double *nabla_f, double *c, double *nabla_c, double *h, double *nabla_h,
+                      int stage, int variant)
+{
+    double ff;
+    nmpc_oracle_model_eval(x, p, stage, 20, variant, &ff, nabla_f, c, nabla_c, h, nabla_h);
+    *f += ff;
+}
+void nmpc_oracle_casadi2forces_normal(double *x, double *y, double *l, double *p, double *f, double *nabla_f, double *c, double *nabla_c,
+                                      double *h, double *nabla_h, double *hess, int stage, int iteration, int thread)
+{
+    (void)y; (void)l; (void)hess; (void)iteration; (void)thread;
+    compat_cb(x, p, f, nabla_f, c, nabla_c, h, nabla_h, stage, 0);
+}
+void nmpc_oracle_casadi2forces_final(double *x, double *y, double *l, double *p, double *f, double *nabla_f, double *c, double *nabla_c,
+                                     double *h, double *nabla_h, double *hess, int stage, int iteration, int thread)
+{
+    (void)y; (void)l; (void)hess; (void)iteration; (void)thread;
+    compat_cb(x, p, f, nabla_f, c, nabla_c, h, nabla_h, stage, 1);
 }

@@ -68,3 +68,67 @@ def total_cost(batch, i, z, model):
         p[0:10] = batch.hdr[i, k]
         f += model(z[k], p, k)["f"]
     return f
+
+
+def kkt_residuals_batch(batch, z, y, zl, zu, lc, variant=0, prefer_reference=True):
+    """ForcesPro's acceptance test for EVERY problem of a batch (oracle/kkt_check.c), driven with the reference's own
+    FORCESNLPsolver_{normal,final}_casadi2forces out of oracle/_ref when that is present (else with the golden-pinned
+    restatement behind the same signature).  Returns (res [B,6], used_reference): columns = stationarity, equality,
+    inequality, complementarity (max |slack * multiplier|), smallest multiplier, cost."""
+    import ctypes
+    import os
+    import subprocess
+    from oracle import oracle as O
+    from oracle import ref_model
+    here = os.path.dirname(os.path.abspath(O.__file__))
+    path = os.path.join(here, "libnmpc_kktcheck.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", here, "libnmpc_kktcheck.so"], stdout=subprocess.DEVNULL)
+    chk = ctypes.CDLL(path)
+    name = "final" if variant else "normal"
+    use_ref = prefer_reference and ref_model.available()
+    if use_ref:
+        cb_lib = ref_model.RefModel(name).lib
+        cb = getattr(cb_lib, f"FORCESNLPsolver_{name}_casadi2forces")
+    else:
+        cb_lib = O._lib(np.float64)
+        cb = getattr(cb_lib, f"nmpc_oracle_casadi2forces_{name}")
+    a = lambda x, dt=np.float64: np.ascontiguousarray(x, dt)
+    B, N, mcap = batch.B, batch.N, batch.mcap
+    xinit, hdr, rows, nrows = a(batch.xinit), a(batch.hdr), a(batch.rows), a(batch.nrows, np.int32)
+    z, y, zl, zu = a(z), a(y), a(zl), a(zu)
+    lc = a(lc) if mcap else np.zeros((B, N, 1))
+    res = np.zeros((B, 6))
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    chk.nmpc_kkt_check.restype = ctypes.c_int
+    chk.nmpc_kkt_check.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 10
+    rc = chk.nmpc_kkt_check(ctypes.cast(cb, ctypes.c_void_p), B, N, mcap, p(xinit), p(hdr), p(rows), p(nrows), p(z), p(y), p(zl),
+                            p(zu), p(lc), p(res))
+    assert rc == 0, rc
+    return res, use_ref
+
+
+def compare_with_slsqp(batch, z, flag, index, z_slsqp, f_slsqp, tol_z=1e-3, tol_f=1e-5):
+    """Our KKT points against an independent solver's (tests/golden/slsqp_kkt_points.npz), instance by instance.
+
+    Per instance: |z - z_slsqp|_inf and the relative objective difference (ours - SLSQP's) / |SLSQP's|, both costs
+    evaluated by the same (golden-pinned) model at points that satisfy the constraints to <= 1e-4 / SLSQP's own tolerance.
+    The NLP is non-convex, so a mismatch is classified, not hidden:
+      same point     |dz| <= tol_z and |df| <= tol_f                                  (SURVEY.md 8c pin 3)
+      slsqp worse    SLSQP stopped at a HIGHER cost (it terminates on a line-search failure near the solution: status 8)
+      ours worse     we stopped at a higher cost than a feasible SLSQP point: a different, worse local minimum -- a finding
+    Returns a dict with the counts, the worst values and the per-instance table."""
+    from oracle import oracle as O
+    rows = []
+    for i, zs, fs in zip(index, z_slsqp, f_slsqp):
+        f_ours = total_cost(batch, int(i), z[i].astype(np.float64), lambda zz, p, k: O.model_eval(zz, p, k, batch.N, batch.variant))
+        dz = float(np.max(np.abs(z[i].astype(np.float64) - zs)))
+        df = (f_ours - float(fs)) / abs(float(fs))
+        kind = "same" if (dz <= tol_z and abs(df) <= tol_f) else ("slsqp_worse" if df < 0 else ("ours_worse" if df > tol_f else "same_cost_other_point"))
+        rows.append(dict(i=int(i), flag=int(flag[i]), dz=dz, df=df, kind=kind))
+    kinds = [r["kind"] for r in rows]
+    return dict(n=len(rows), n_same_point=kinds.count("same"), n_slsqp_worse=kinds.count("slsqp_worse"),
+                n_ours_worse=kinds.count("ours_worse"), n_same_cost_other_point=kinds.count("same_cost_other_point"),
+                max_dz_same=max([r["dz"] for r in rows if r["kind"] == "same"], default=0.0),
+                max_abs_df_same=max([abs(r["df"]) for r in rows if r["kind"] == "same"], default=0.0),
+                not_same=[r for r in rows if r["kind"] != "same"])

@@ -225,6 +225,89 @@ def test_cpp_dropin_demo_runs_the_planner_call_sequence():
     assert out.stdout.count("64/64 accepted") == 3 and out.stdout.count("corridor overflow 0") == 3, out.stdout
 
 
+@pytest.mark.parametrize("maker,kw,mixed", [(W.config2, dict(B=4096), False), (W.config3, dict(B=4096), False),
+                                            (W.config2, dict(B=1024, variant=1), False),
+                                            (W.config2, dict(B=4096), True), (W.config3, dict(B=4096), True),
+                                            (W.config2, dict(B=1024, variant=1), True)])
+def test_whole_batch_passes_forcespro_acceptance_with_reference_callbacks(maker, kw, mixed):
+    """Tier bar #1 at BASELINE size: EVERY problem of config 2 (4096), config 3 (4096 of its 65536) and the final
+    variant (1024) -- through the fp64 kernel and through the mixed-precision kernel -- is re-evaluated with the
+    reference's own casadi2forces callbacks (oracle/_ref; oracle/kkt_check.c) at the returned point and multipliers:
+    the four inf-norms ForcesPro stops on are <= 1e-4, every multiplier is non-negative (a sign-blind complementarity
+    check would let a negative one through), and the residuals the kernel reports are the ones recomputed here."""
+    b = maker(**kw)
+    res, mult = S.solve_with_multipliers(b, mixed=mixed)
+    assert np.all(res.flag == 1)
+    chk, used_ref = H.kkt_residuals_batch(b, res.z, mult["y"], mult["zl"], mult["zu"], mult["lc"], variant=b.variant)
+    assert used_ref == ref_model.available()
+    assert chk[:, 0:4].max() <= TOL * (1 + 1e-9), chk[:, 0:4].max(0)
+    assert chk[:, 4].min() >= 0.0, chk[:, 4].min()
+    assert np.max(np.abs(chk[:, 0] - res.info_real[:, 2])) < 1e-6 and np.max(np.abs(chk[:, 1] - res.info_real[:, 0])) < 1e-7
+    assert np.max(np.abs(chk[:, 5] - res.info_real[:, 4])) <= 1e-9 * np.max(np.abs(chk[:, 5]))     # pobj is the reference's cost
+
+
+def test_long_horizon_config4_matches_oracle_at_4096_problems():
+    """BASELINE config 4 (N = 40; no reference counterpart exists: N = 20 is baked into its ABI) on a 64 x 64 wind sweep =
+    4096 problems: the fp64 kernel against the CPU port (same algorithm, dense Riccati in double precision -- oracle
+    opts.mixed = 2, which itself walks the Schur restatement's path iteration for iteration), and the mixed-precision
+    kernel against both."""
+    b = W.config4(64, 40)
+    c = O.solve_batch(b, opts=O.default_opts(mixed=2))
+    assert np.all(c["flag"] == 1)
+    _compare(S.solve_host(b), c, frac_same_it=0.98)
+    m = S.solve_host(b, np.float32)
+    assert np.all(m.flag == 1) and m.resolved.mean() < 0.02
+    dz = np.abs(m.z.astype(np.float64) - c["z"]).reshape(b.B, -1).max(1)
+    assert dz.max() < 2e-3 and np.median(dz) < 2e-5, (dz.max(), np.median(dz))
+    assert abs(m.it.mean() - c["it"].mean()) < 0.03 * c["it"].mean()
+
+
+def test_infeasible_initial_state_is_reported_not_solved():
+    """xinit outside a stage-0 corridor row, or outside a bound: the stage-0 states are fixed by the xinit equality, so the
+    reference's NLP has no feasible point.  Stated behaviour (include/nmpc_b200.h): NOPROGRESS (-7) after zero iterations
+    with the violation in res_ineq -- from the fp64 kernel, the mixed-precision kernel, the reference-named symbol and the
+    CPU port alike; neighbours in the same batch are unaffected, and a violation within TolIneq is not an error."""
+    b = W.config2(8)
+    base = S.solve_host(b)
+    bad = W.Batch(b.xinit.copy(), b.z0.copy(), b.hdr.copy(), b.rows.copy(), b.nrows.copy(), b.variant)
+    # problem 2: 0.3 m beyond row 0 of its stage-0 polytope; problem 5: vertical speed beyond the 2 m/s bound
+    a0 = bad.rows[2, 0, 0, 0:3]
+    bad.xinit[2, 0:3] += a0 * (bad.rows[2, 0, 0, 3] - a0 @ bad.xinit[2, 0:3] + 0.3)
+    bad.z0[2, :, 8:11] = bad.xinit[2, 0:3]
+    bad.xinit[5, 5] = 2.5; bad.z0[5, :, 13] = 2.5
+    # problem 6: on the row within tolerance (5e-5 beyond b + hu): still a valid problem
+    a6 = bad.rows[6, 0, 1, 0:3]
+    bad.xinit[6, 0:3] += a6 * (bad.rows[6, 0, 1, 3] + 1e-5 - a6 @ bad.xinit[6, 0:3] + 5e-5)
+    bad.z0[6, :, 8:11] = bad.xinit[6, 0:3]
+    for r in (S.solve_host(bad), S.solve_host(bad, mixed=True), S.solve_host(bad, np.float32)):
+        assert list(r.flag[[2, 5]]) == [-7, -7] and list(r.it[[2, 5]]) == [0, 0]
+        assert abs(r.info_real[2, 1] - (0.3 - 1e-5)) < 1e-6 and abs(r.info_real[5, 1] - 0.5) < 1e-6
+        keep = [0, 1, 3, 4, 7]
+        assert np.all(r.flag[keep] == 1) and r.flag[6] == 1
+        if r.z.dtype == np.float64:
+            assert np.max(np.abs(r.z[keep] - base.z[keep])) < 1e-3
+    c = O.solve_batch(bad)
+    assert list(c["flag"][[2, 5]]) == [-7, -7] and c["flag"][6] == 1
+    w = forces.FORCESNormal()
+    xinit, x0, allp = W.to_forces_params(bad, 2)
+    w.params_.xinit[:] = xinit.tolist(); w.params_.x0[:] = x0.tolist(); w.params_.all_parameters[:] = allp.tolist()
+    assert w.solve_params() == -7 and w.info_.it == 0 and abs(w.info_.res_ineq - (0.3 - 1e-5)) < 1e-6
+
+
+def test_kkt_points_match_independent_slsqp_solutions():
+    """SURVEY.md 7-1d / 8c pin 3 on the device: 100 instances solved by scipy SLSQP driving the reference's callbacks
+    (tests/golden/slsqp_kkt_points.npz, made by tests/golden/make_slsqp_golden.py) against the fp64 kernel and the
+    mixed-precision kernel.  Every instance is reported; see test_oracle_solver.py for the same check of the CPU port."""
+    g = np.load(os.path.join(GOLD_DIR, "slsqp_kkt_points.npz"))
+    for name, maker in (("config2", lambda: W.config2(60)), ("config3", lambda: W.config3(40))):
+        sel = g["workload"] == name
+        b = maker()
+        for r in (S.solve_host(b), S.solve_host(b, mixed=True)):
+            rep = H.compare_with_slsqp(b, r.z, r.flag, g["index"][sel], g["z"][sel], g["fun"][sel])
+            assert rep["n"] == int(sel.sum()) and rep["n_same_point"] >= rep["n"] - rep["n_slsqp_worse"], rep
+            assert rep["n_ours_worse"] == 0, rep
+
+
 MIXED_CASES = [(W.config2, dict(B=512)), (W.config3, dict(B=1024)), (W.config2, dict(B=128, variant=1)),
                (W.config4, dict(side=16, n_stages=40))]
 
@@ -333,10 +416,12 @@ def test_failed_agent_leaves_nothing_behind_and_restarts_cold():
             hist.append((cmd.copy(), flag.copy(), it.copy()))
             if inject and step == 4:
                 assert flag[3] in (-6, -7) and np.all(np.delete(flag, 3) == 1)
-                assert not np.all(np.isfinite(s.z[3].cpu().numpy()))           # the failed output really is garbage ...
+                bad_out = s.z[3].cpu().numpy().copy()                          # whatever the failed solve left behind ...
             if inject and step == 5:
                 zp = s.zprev.cpu().numpy()
-                assert np.all(np.isfinite(zp))                                 # ... and never entered the plan in force
+                assert np.all(np.isfinite(zp))                                 # ... never entered the plan in force:
+                cold = np.zeros(17); cold[3] = cold[7] = 7.3                   # agent 3 holds the cold guess at its state
+                assert np.array_equal(zp[3, :, 0:8], np.tile(cold[0:8], (b.N, 1))) and not np.array_equal(zp[3], bad_out)
                 assert flag[3] == 1 and it[3] > hist[3][2][3]                  # cold restart: more iterations than a warm one
         runs.append(hist)
     clean, faulty = runs
