@@ -275,10 +275,12 @@ def test_infeasible_initial_state_is_reported_not_solved():
     bad.xinit[2, 0:3] += a0 * (bad.rows[2, 0, 0, 3] - a0 @ bad.xinit[2, 0:3] + 0.3)
     bad.z0[2, :, 8:11] = bad.xinit[2, 0:3]
     bad.xinit[5, 5] = 2.5; bad.z0[5, :, 13] = 2.5
-    # problem 6: on the row within tolerance (5e-5 beyond b + hu): still a valid problem
-    a6 = bad.rows[6, 0, 1, 0:3]
-    bad.xinit[6, 0:3] += a6 * (bad.rows[6, 0, 1, 3] + 1e-5 - a6 @ bad.xinit[6, 0:3] + 5e-5)
-    bad.z0[6, :, 8:11] = bad.xinit[6, 0:3]
+    # problem 6: at rest, 5e-5 beyond the BACK plane of its box (row 3, two metres behind the start of the reference):
+    # within TolIneq, so still a valid problem -- and a solvable one, the reference pulls it inside
+    a6 = bad.rows[6, 0, 3, 0:3]
+    bad.xinit[6, 0:3] += a6 * (bad.rows[6, 0, 3, 3] + 1e-5 - a6 @ bad.xinit[6, 0:3] + 5e-5)
+    bad.xinit[6, 3:6] = 0.0
+    bad.z0[6, :, 8:17] = bad.xinit[6]
     for r in (S.solve_host(bad), S.solve_host(bad, mixed=True), S.solve_host(bad, np.float32)):
         assert list(r.flag[[2, 5]]) == [-7, -7] and list(r.it[[2, 5]]) == [0, 0]
         assert abs(r.info_real[2, 1] - (0.3 - 1e-5)) < 1e-6 and abs(r.info_real[5, 1] - 0.5) < 1e-6
