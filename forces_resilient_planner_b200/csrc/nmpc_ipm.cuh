@@ -501,8 +501,8 @@ template <typename T, int N, bool PC = false> struct Solver {
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const int e = lane + 32 * t;
-            int i = 0;
-            while ((i + 1) * (i + 2) / 2 <= e) i++;
+            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);      // row of packed-lower entry e
+            i += ((i + 1) * (i + 2) / 2 <= e) - (i * (i + 1) / 2 > e);           // guard the rounding of the root
             const int j = e - i * (i + 1) / 2;
             ti[t] = i; tj[t] = j;
             // phase D (xi-ordering): where the additive terms of P_k[i][j] live (-1: none)
@@ -533,36 +533,47 @@ template <typename T, int N, bool PC = false> struct Solver {
                 }
                 __syncwarp();
                 // ---- phase B: lane = column of PF (v-ordering); lane 13 = the vector tv ----------
-                T g[13];
+                // g = F' (column), then ONE instruction stream for all fourteen lanes turns it into what phases C / D read:
+                //   lanes 0-3  (u columns)  Q_uu column (+ P+_qq + PF_qu + PF_qu' + Phi_uu) and the Q_ux row
+                //   lanes 4-12 (x columns)  column of Q_xx
+                //   lane 13    (vector tv)  q~_u = g + g_k,u + tv_q and q~_x = g + g_k,x
+                // the three groups differ only in per-lane base pointers / strides and a few predicated loads (no
+                // divergent branches: they used to run one after the other)
                 if (lane < 14) {
+                    const bool isU = lane < 4, isV = lane == 13, isX = !isU && !isV;
+                    const int j = lane & 3;
                     const T* col = lane < 13 ? PF + lane : TV;
                     const int cs = lane < 13 ? 13 : 1;
                     const T xp[3] = {col[0], col[cs], col[2 * cs]}, xv[3] = {col[3 * cs], col[4 * cs], col[5 * cs]};
                     const T xa[3] = {col[6 * cs], col[7 * cs], col[8 * cs]};
+                    T g[13];
                     ft_times(jc, xp, xv, xa, g);
-                    if (lane < 4) {                                // column of Q_uu and of Q_xu = Q_ux'
-                        const int j = lane;
+                    const T* pA = isV ? gk : PN + (9 * 13 + 9 + j);
+                    const T* pB = isV ? TV + 9 : PF + (9 * 13 + j);
+                    const int sAB = isV ? 1 : 13;
+                    const T* pC = PF + (9 + j) * 13;
+                    if (!isX) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            T acc = g[i] + (PN[(9 + i) * 13 + 9 + j] + (PF[(9 + i) * 13 + j] + PF[(9 + j) * 13 + i]));
-                            if (i == j) acc += phi[i];
-                            QUU[i * 4 + j] = acc;
+                            T acc = g[i] + (pA[i * sAB] + (pB[i * sAB] + (isU ? pC[i] : T(0))));
+                            if (isU && i == j) acc += phi[i];
+                            g[i] = acc;
                         }
+                        const T* pE = isU ? pC : gk + 4;
 #pragma unroll
-                        for (int i = 4; i < 13; i++) QUR[j * 13 + i - 4] = g[i] + PF[(9 + j) * 13 + i];
-                    } else if (lane == 13) {                       // q~ = g + F' tv (+ the q+ = u part of tv)
-#pragma unroll
-                        for (int w = 0; w < 4; w++) QV[w] = g[w] + (gk[w] + TV[9 + w]);
-#pragma unroll
-                        for (int w = 4; w < 13; w++) QXI[w - 4] = g[w] + gk[w + 4];
+                        for (int i = 4; i < 13; i++) g[i] += pE[i];
                     }
-                } else if (lane >= 16 && lane < 20) {
-                    QXI[9 + lane - 16] = gk[4 + lane - 16];
-                }
-                if (PC) __syncwarp();                              // GG overwrites PF: every read of PF is behind us
-                if (lane >= 4 && lane < 13) {                      // column of Q_xx (phase D reads the lower triangle)
+                    if (PC) __syncwarp(0x3fffu);                   // GG overwrites PF: every read of PF is behind us
+                    if (!isX) {
+                        T* dT = isV ? QV : QUU + j;
+                        const int sT = isV ? 1 : 4;
 #pragma unroll
-                    for (int i = 4; i < 13; i++) GG[i * 13 + lane] = g[i];
+                        for (int i = 0; i < 4; i++) dT[i * sT] = g[i];
+                    }
+                    T* dB = isU ? QUR + (j * 13 - 4) : (isV ? QXI - 4 : GG + lane);
+                    const int sD = isX ? 13 : 1;
+#pragma unroll
+                    for (int i = 4; i < 13; i++) dB[i * sD] = g[i];
                 }
                 if (lane < 16) QUR[(lane >> 2) * 13 + 9 + (lane & 3)] = ((lane >> 2) == (lane & 3)) ? phi[20] : T(0);
             } else {
@@ -622,7 +633,8 @@ template <typename T, int N, bool PC = false> struct Solver {
                     PN[j * 13 + i] = v;
                 } else if (e >= 91 && e < 104) {
                     const int i = e - 91;
-                    P[k * NXI + i] = QXI[i] - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
+                    const T qxi = (i < 9) ? QXI[i] : gk[i - 5];    // the u_prev rows of q~ are the stage gradient itself
+                    P[k * NXI + i] = qxi - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
                 }
             }
             __syncwarp();

@@ -30,7 +30,8 @@ from .solver import _check
 
 class RecedingHorizonStream:
     def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True,
-                 wrap_yaw: bool = False, dynamic_ellipsoids: bool = False, longest_first: bool = True):
+                 wrap_yaw: bool = False, dynamic_ellipsoids: bool = False, longest_first: bool = True,
+                 mixed: bool = False):
         import torch
         self.torch = torch
         self.dev = torch.device(device)
@@ -73,6 +74,10 @@ class RecedingHorizonStream:
         # agents, which restart cold, first).  CTAs start in index order, so the agents that spill into the
         # second wave (1024 agents > 148 x 6 resident warps) are the quick ones and the launch ends sooner.
         self.longest_first = longest_first
+        # True: the replans run the mixed-precision kernel (nmpc_solve_batch_mixed_f64: same tolerances, 25.8 KB instead of
+        # 36.4 KB of shared memory per agent -> 1184 instead of 888 resident agents per GPU, so a 1024-agent fleet is ONE
+        # wave, and every iteration is shorter); its fp64 re-solve of an agent it gives up on rides on the same stream
+        self.mixed = mixed
         self.order = torch.arange(self.B, dtype=torch.int32, device=self.dev)
         self.cycle = 0
 
@@ -100,13 +105,16 @@ class RecedingHorizonStream:
         if warm and self.longest_first:
             prep.rank_longest_first(self.info_int, self.order, stream=stream)
             order = self.order.data_ptr()
-        fn = self.lib.nmpc_solve_batch_ordered_f64
-        fn.restype = ctypes.c_int
-        fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + \
-            [ctypes.c_void_p] * 5
-        _check(fn(self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(), hdr.data_ptr(), rows.data_ptr(),
-                  nrows.data_ptr(), 0, ctypes.byref(o), self.z.data_ptr(), self.info_int.data_ptr(),
-                  self.info_real.data_ptr(), order, ctypes.c_void_p(stream.cuda_stream)))
+        args = [self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(), hdr.data_ptr(), rows.data_ptr(),
+                nrows.data_ptr(), 0, ctypes.byref(o), self.z.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr()]
+        if self.mixed:
+            _check(self.lib.nmpc_solve_batch_mixed_f64(*args, None, None, None, None, order, ctypes.c_void_p(stream.cuda_stream)))
+        else:
+            fn = self.lib.nmpc_solve_batch_ordered_f64
+            fn.restype = ctypes.c_int
+            fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + \
+                [ctypes.c_void_p] * 5
+            _check(fn(*args, order, ctypes.c_void_p(stream.cuda_stream)))
 
     def replan(self, ref_pos: np.ndarray, ref_yaw: np.ndarray, ext_acc: np.ndarray):
         """One cycle.  Host arrays in (refs of this cycle), host arrays out (first command, flags).

@@ -17,6 +17,7 @@ ap.add_argument("--agents", type=int, default=1024)
 ap.add_argument("--replans", type=int, default=500)
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--ellipsoids", action="store_true", help="propagate the disturbance ellipsoids on the device every replan")
+ap.add_argument("--mixed", action="store_true", help="replans through the mixed-precision kernel (nmpc_solve_batch_mixed_f64)")
 a = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local)
@@ -24,7 +25,7 @@ dev = torch.device("cuda", local)
 lo, hi = D.shard_range(a.agents, rank, world)
 batch = W.config2(a.agents).slice(lo, hi)            # the same fleet whatever the number of GPUs
 rng = np.random.Generator(np.random.PCG64(W.SEED + 5 + 1000 * rank))
-s = ST.RecedingHorizonStream(batch, device=f"cuda:{local}", use_graph=not a.no_graph, dynamic_ellipsoids=a.ellipsoids)
+s = ST.RecedingHorizonStream(batch, device=f"cuda:{local}", use_graph=not a.no_graph, dynamic_ellipsoids=a.ellipsoids, mixed=a.mixed)
 ext = batch.hdr[:, 0, 3:6].copy()
 lat, its, fails, resets = [], [], 0, 0
 gcmd = torch.empty((a.agents, 5), dtype=torch.float64, device=dev) if world > 1 else None
