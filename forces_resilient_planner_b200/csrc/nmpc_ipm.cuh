@@ -515,7 +515,14 @@ template <typename T, int N, bool PC = false> struct Solver {
             const T* phi = PHID + k * L::PHI_S;
             const T* gk = G + k * NZ;
             if (nx) {
-                const T* jc = JC + k * NJC;
+                // single precision: the 51 Jacobian words of the stage are read once into registers and serve both
+                // products (phases A and B); double precision has no registers to spare (122 hold the parked state)
+                T jreg[sizeof(T) == 4 ? NJC : 1];
+                if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                    for (int e = 0; e < NJC; e++) jreg[e] = JC[k * NJC + e];
+                }
+                const T* jc = sizeof(T) == 4 ? jreg : JC + k * NJC;
                 // ---- phase A: lane = row of P+ (xi-ordering) ----------------------------------
                 if (lane < NXI) {
                     const T* pr = PN + lane * 13;
