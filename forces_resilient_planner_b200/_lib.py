@@ -28,7 +28,7 @@ class EllipsoidConsts(ctypes.Structure):
 EXPORTS = [
     "nmpc_default_opts", "nmpc_last_error", "nmpc_version", "nmpc_supported_horizon",
     "nmpc_smem_bytes", "nmpc_smem_bytes_pc", "nmpc_solve_batch_f64", "nmpc_solve_batch_f32",
-    "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64", "nmpc_solve_batch_mixed_f64",
+    "nmpc_solve_batch_ex_f64", "nmpc_solve_batch_ordered_f64", "nmpc_solve_batch_mixed_f64", "nmpc_solve_batch_lowlatency_f64",
     "nmpc_solve_batch_host_f64", "nmpc_solve_batch_host_f32", "nmpc_solve_batch_host_mixed_f64", "nmpc_model_eval_host_f64",
     "nmpc_riccati_factor_f64", "nmpc_riccati_factor_f32",
     "nmpc_kkt_backsolve_f64", "nmpc_kkt_backsolve_f32", "nmpc_backsolve_factor_words",
@@ -65,8 +65,9 @@ def load() -> ctypes.CDLL:
         getattr(lib, name).restype = _i
     lib.nmpc_solve_batch_ex_f64.argtypes = sig + [_vp] * 5
     lib.nmpc_solve_batch_ex_f64.restype = _i
-    lib.nmpc_solve_batch_mixed_f64.argtypes = sig + [_vp] * 6
-    lib.nmpc_solve_batch_mixed_f64.restype = _i
+    for name in ("nmpc_solve_batch_mixed_f64", "nmpc_solve_batch_lowlatency_f64"):
+        getattr(lib, name).argtypes = sig + [_vp] * 6
+        getattr(lib, name).restype = _i
     _lib = lib
     return lib
 

@@ -26,6 +26,7 @@
 #include "nmpc_ellipsoid.cuh"
 #include "nmpc_ipm.cuh"
 #include "nmpc_ipm_mixed.cuh"
+#include "nmpc_ipm_group.cuh"
 #include "nmpc_prep.cuh"
 
 // ---- the ABI contract of the reference headers --------------------------------
@@ -108,6 +109,17 @@ int launch_mixed(const nmpc::MixedParams& prm, cudaStream_t st)
     return 0;
 }
 
+template <int N>
+int launch_group(const nmpc::MixedParams& prm, cudaStream_t st)
+{
+    const size_t smem = nmpc::GLayout<N>::bytes(prm.mcap);
+    static thread_local size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_smem(nmpc::nmpc_ipm_group_kernel<N>, smem, configured)) return rc;
+    nmpc::nmpc_ipm_group_kernel<N><<<prm.B, nmpc::GROUP_THREADS, smem, st>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // order[0 .. *count) <- the problems whose exit flag is not 1 (optimal); one pass, order of arrival
 __global__ void collect_unsolved_kernel(int B, const int* info_int, int* count, int* order)
 {
@@ -162,7 +174,7 @@ int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, cons
 int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
                 const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int, void* info_real,
                 void* stream, int io32, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
-                void* lc_out = nullptr, const int* order = nullptr)
+                void* lc_out = nullptr, const int* order = nullptr, bool group = false)
 {
     nmpc_opts o;
     if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
@@ -174,7 +186,9 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
     std::memcpy(&prm.o, &o, sizeof(o));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (int rc = (N == 20 ? launch_mixed<20>(prm, st) : launch_mixed<40>(prm, st))) return rc;
+    // group: the low-latency variant, one warp-group (128 threads) per problem (nmpc_ipm_group.cuh)
+    if (int rc = group ? (N == 20 ? launch_group<20>(prm, st) : launch_group<40>(prm, st))
+                       : (N == 20 ? launch_mixed<20>(prm, st) : launch_mixed<40>(prm, st))) return rc;
     if (o.mixed < 0) return 0;                      // opts.mixed = -1: no fp64 safety net (tests, profiling)
     int* ws = nullptr;
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), ((size_t)B + 4) * sizeof(int), st));
@@ -602,6 +616,14 @@ int nmpc_solve_batch_mixed_f64(int B, int N, int mcap, const double* xinit, cons
 {
     return solve_mixed(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream, 0,
                        y_out, zl_out, zu_out, lc_out, order);
+}
+int nmpc_solve_batch_lowlatency_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
+                                    const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,
+                                    int* info_int, double* info_real, double* y_out, double* zl_out, double* zu_out,
+                                    double* lc_out, const int* order, void* cuda_stream)
+{
+    return solve_mixed(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, cuda_stream, 0,
+                       y_out, zl_out, zu_out, lc_out, order, true);
 }
 int nmpc_solve_batch_ex_f64(int B, int N, int mcap, const double* xinit, const double* z0, const double* hdr,
                             const double* rows, const int* nrows, int variant, const nmpc_opts* opts, double* z_out,

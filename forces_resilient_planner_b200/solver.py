@@ -107,9 +107,11 @@ class DeviceBatch:
                       self.info_real.cpu().numpy(), ii[:, 3].copy())
 
 
-def solve_device(db: DeviceBatch, opts: _lib.NmpcOpts | None = None, stream=None, mixed: bool = False) -> None:
+def solve_device(db: DeviceBatch, opts: _lib.NmpcOpts | None = None, stream=None, mixed: bool = False,
+                 lowlatency: bool = False) -> None:
     """Enqueue one solve on `stream` (default: torch's current stream): the fp64 kernel for float64 batches, the
-    mixed-precision kernel (+ its fp64 re-solve of the few problems it gives up on) for float32 batches or `mixed`."""
+    mixed-precision kernel (+ its fp64 re-solve of the few problems it gives up on) for float32 batches or `mixed`;
+    `lowlatency` (float64 batches): the warp-group variant of the mixed-precision kernel (nmpc_solve_batch_lowlatency_f64)."""
     lib = _lib.load()
     torch = db.torch
     st = stream if stream is not None else torch.cuda.current_stream(db.device)
@@ -121,20 +123,22 @@ def solve_device(db: DeviceBatch, opts: _lib.NmpcOpts | None = None, stream=None
     with torch.cuda.device(db.device):
         if db.np_dtype == np.float32:
             _check(lib.nmpc_solve_batch_f32(*args, ctypes.c_void_p(st.cuda_stream)))
+        elif lowlatency:
+            _check(lib.nmpc_solve_batch_lowlatency_f64(*args, None, None, None, None, None, ctypes.c_void_p(st.cuda_stream)))
         elif mixed:
             _check(lib.nmpc_solve_batch_mixed_f64(*args, None, None, None, None, None, ctypes.c_void_p(st.cuda_stream)))
         else:
             _check(lib.nmpc_solve_batch_f64(*args, ctypes.c_void_p(st.cuda_stream)))
 
 
-def solve(batch: Batch, dtype=np.float64, opts=None, device="cuda:0", mixed: bool = False) -> Result:
+def solve(batch: Batch, dtype=np.float64, opts=None, device="cuda:0", mixed: bool = False, lowlatency: bool = False) -> Result:
     """Convenience: upload, solve on the device, download."""
     db = DeviceBatch(batch, dtype, device)
-    solve_device(db, opts, mixed=mixed)
+    solve_device(db, opts, mixed=mixed, lowlatency=lowlatency)
     return db.result()
 
 
-def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0", mixed: bool = False):
+def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0", mixed: bool = False, lowlatency: bool = False):
     """fp64-array solve that also returns the multipliers of the KKT point (nmpc_solve_batch_ex_f64, or
     nmpc_solve_batch_mixed_f64 with `mixed`).
 
@@ -154,7 +158,9 @@ def solve_with_multipliers(batch: Batch, opts=None, device="cuda:0", mixed: bool
                 d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o),
                 db.z.data_ptr(), db.info_int.data_ptr(), db.info_real.data_ptr(),
                 y.data_ptr(), zl.data_ptr(), zu.data_ptr(), lc.data_ptr() if db.mcap else None]
-        if mixed:
+        if lowlatency:
+            _check(lib.nmpc_solve_batch_lowlatency_f64(*args, None, ctypes.c_void_p(st.cuda_stream)))
+        elif mixed:
             _check(lib.nmpc_solve_batch_mixed_f64(*args, None, ctypes.c_void_p(st.cuda_stream)))
         else:
             _check(lib.nmpc_solve_batch_ex_f64(*args, ctypes.c_void_p(st.cuda_stream)))

@@ -31,7 +31,7 @@ from .solver import _check
 class RecedingHorizonStream:
     def __init__(self, batch: W.Batch, device="cuda:0", mu0_warm: float = 0.1, use_graph: bool = True,
                  wrap_yaw: bool = False, dynamic_ellipsoids: bool = False, longest_first: bool = True,
-                 mixed: bool = False):
+                 mixed: bool = False, lowlatency: bool | None = None):
         import torch
         self.torch = torch
         self.dev = torch.device(device)
@@ -78,6 +78,11 @@ class RecedingHorizonStream:
         # 36.4 KB of shared memory per agent -> 1184 instead of 888 resident agents per GPU, so a 1024-agent fleet is ONE
         # wave, and every iteration is shorter); its fp64 re-solve of an agent it gives up on rides on the same stream
         self.mixed = mixed
+        # the warp-group kernel (nmpc_solve_batch_lowlatency_f64: 128 threads per agent, ~0.7x the time per iteration)
+        # pays when the fleet leaves most of the GPU idle; default: on for mixed streams of at most 2 agents per SM
+        if lowlatency is None:
+            lowlatency = mixed and self.B <= 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self.lowlatency = bool(lowlatency)
         self.order = torch.arange(self.B, dtype=torch.int32, device=self.dev)
         self.cycle = 0
 
@@ -107,7 +112,9 @@ class RecedingHorizonStream:
             order = self.order.data_ptr()
         args = [self.B, self.N, self.mcap, self.xinit.data_ptr(), self.z0.data_ptr(), hdr.data_ptr(), rows.data_ptr(),
                 nrows.data_ptr(), 0, ctypes.byref(o), self.z.data_ptr(), self.info_int.data_ptr(), self.info_real.data_ptr()]
-        if self.mixed:
+        if self.lowlatency:
+            _check(self.lib.nmpc_solve_batch_lowlatency_f64(*args, None, None, None, None, order, ctypes.c_void_p(stream.cuda_stream)))
+        elif self.mixed:
             _check(self.lib.nmpc_solve_batch_mixed_f64(*args, None, None, None, None, order, ctypes.c_void_p(stream.cuda_stream)))
         else:
             fn = self.lib.nmpc_solve_batch_ordered_f64

@@ -115,6 +115,17 @@ int nmpc_solve_batch_mixed_f64(int B, int N, int mcap, const double *xinit, cons
                                double *y_out, double *zl_out, double *zu_out, double *lc_out,
                                const int *order, void *cuda_stream);
 
+/* Low-latency variant of nmpc_solve_batch_mixed_f64 (same arguments, same algorithm, tolerances and exit codes): one
+ * warp-GROUP (128 threads) per problem instead of one warp (csrc/nmpc_ipm_group.cuh).  For small fleets -- fewer
+ * problems than the GPU has SMs x a few, e.g. BASELINE config 5 at 128 agents per GPU -- where the latency of one
+ * solve, not the throughput of thousands, is what the caller waits for: an interior-point iteration takes about half
+ * the time of the one-warp kernels'.  With thousands of problems the one-warp kernels are the faster choice.      */
+int nmpc_solve_batch_lowlatency_f64(int B, int N, int mcap, const double *xinit, const double *z0,
+                                    const double *hdr, const double *rows, const int *nrows, int variant,
+                                    const nmpc_opts *opts, double *z_out, int *info_int, double *info_real,
+                                    double *y_out, double *zl_out, double *zu_out, double *lc_out,
+                                    const int *order, void *cuda_stream);
+
 /* as nmpc_solve_batch_f64, additionally returning the multipliers of the KKT point (any of the
  * four may be NULL): y_out [B][N][13] (c-ordering [x+(9); u(4)], y[0] = 0), zl_out / zu_out
  * [B][N][17], lc_out [B][N][mcap].  Used to check ForcesPro's acceptance test with the

@@ -337,6 +337,27 @@ def test_mixed_precision_meets_the_reference_tolerances(maker, kw):
     assert np.mean(np.abs(res.it[same] - m["it"][same]) <= 1) >= 0.97
 
 
+@pytest.mark.parametrize("maker,kw", [(W.config2, dict(B=300)), (W.config3, dict(B=300)), (W.config2, dict(B=64, variant=1)),
+                                      (W.config4, dict(side=12, n_stages=40)), (W.config1, dict())])
+def test_warp_group_kernel_is_the_mixed_kernel_spread_over_128_threads(maker, kw):
+    """nmpc_solve_batch_lowlatency_f64 (one warp-group per problem) against the one-warp mixed-precision kernel and the fp64
+    CPU port: same exit flags, same KKT points (both stop inside the 1e-4 residual ball: |dz| <= 1e-3 vs fp64), iteration
+    counts equal to the one-warp kernel's on >= 97 % of the problems (the two sweeps round differently), and every point
+    passes ForcesPro's acceptance test with the reference callbacks."""
+    b = maker(**kw)
+    c = O.solve_batch(b)
+    w = S.solve(b, mixed=True)
+    g, mult = S.solve_with_multipliers(b, lowlatency=True)
+    assert np.array_equal(g.flag, c["flag"]) and np.all(g.flag == 1)
+    dz = np.abs(g.z - c["z"]).reshape(b.B, -1).max(1)
+    assert dz.max() < 1e-3 and np.median(dz) < 2e-5
+    assert np.mean(np.abs(g.it - w.it) <= 1) >= 0.97 and abs(g.it.mean() - c["it"].mean()) < 0.05 * c["it"].mean()
+    assert np.all(g.info_real[:, 0:4] <= TOL)
+    if b.N == 20:
+        chk, _ = H.kkt_residuals_batch(b, g.z, mult["y"], mult["zl"], mult["zu"], mult["lc"], variant=b.variant)
+        assert chk[:, 0:4].max() <= TOL * (1 + 1e-9) and chk[:, 4].min() >= 0.0
+
+
 def test_mixed_precision_kkt_points_pass_forcespro_acceptance_with_reference_callbacks():
     for b in (W.config3(96), W.config2(48, variant=1)):
         res, mult = S.solve_with_multipliers(b, mixed=True)
@@ -447,6 +468,32 @@ def test_rank_longest_first_equals_stable_argsort():
         want = np.argsort(-key, kind="stable").astype(np.int32)
         got = prep.rank_longest_first(torch.from_numpy(ii).cuda(), torch.empty(B, dtype=torch.int32, device="cuda")).cpu().numpy()
         assert np.array_equal(got, want), B
+
+
+@pytest.mark.parametrize("B,expect_group", [(40, True), (400, False)])
+def test_mixed_precision_stream_follows_the_fp64_closed_loop(B, expect_group):
+    """The receding-horizon stream through the mixed-precision kernels (warp-group kernel for a small fleet, one-warp
+    kernel for a large one) against the same stream through the fp64 kernel: every replan converges, the commands agree
+    to the solver tolerance, the iteration counts agree on >= 95 % of the (agent, replan) pairs."""
+    from forces_resilient_planner_b200 import stream as ST
+    b = W.config2(B)
+    runs = []
+    for mixed in (False, True):
+        rng = np.random.Generator(np.random.PCG64(17))
+        s = ST.RecedingHorizonStream(b, use_graph=True, mixed=mixed)
+        assert s.lowlatency == (mixed and expect_group)
+        ext = b.hdr[:, 0, 3:6].copy()
+        hist = []
+        for step in range(10):
+            ref, yaw, ext = ST.synthetic_refs(b, step, rng, ext)
+            hist.append(s.replan(ref, yaw, ext))
+        runs.append(hist)
+    same = []
+    for (c0, f0, i0), (c1, f1, i1) in zip(*runs):
+        assert np.all(f0 == 1) and np.all(f1 == 1)
+        assert np.max(np.abs(c0 - c1)) < 5e-3
+        same.append(np.mean(i0 == i1))
+    assert np.mean(same) >= 0.95
 
 
 def test_stream_with_propagated_ellipsoids_matches_cpu_closed_loop():
