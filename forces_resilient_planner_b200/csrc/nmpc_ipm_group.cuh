@@ -1,4 +1,4 @@
-// nmpc_ipm_group.cuh -- low-latency variant of the mixed-precision solve: one WARP-GROUP (4 warps = one CTA of 128
+// nmpc_ipm_group.cuh -- low-latency variant of the mixed-precision solve: one WARP-GROUP (8 warps = one CTA of 256
 // threads) owns one MPC instance.
 //
 // Same drop-in role, algorithm, tolerances and exit codes as nmpc_ipm_mixed.cuh (FORCESNLPsolver_{normal,final}_solve,
@@ -6,15 +6,16 @@
 // fp64 iterate / model / residuals / line search, fp32 Newton system in delta form).  The one-warp kernels are built for
 // THROUGHPUT: thousands of problems, every SM full, the latency of one problem's iteration (~57 us) hidden behind its
 // neighbours.  A receding-horizon fleet of a few hundred vehicles (BASELINE config 5 at 128 agents per GPU) leaves the
-// SMs nearly empty, and then the latency of ONE solve is all that counts.  Here a problem's iteration is spread over 128
+// SMs nearly empty, and then the latency of ONE solve is all that counts.  Here a problem's iteration is spread over 256
 // threads wherever the work allows:
 //
-//   * "flat" phases (bounds, multipliers, steps: 17 N independent (stage, variable) pairs) -- 3 rounds instead of 11;
+//   * "flat" phases (bounds, multipliers, steps: 17 N independent (stage, variable) pairs) -- 2 rounds instead of 11;
 //   * corridor-row phases -- four threads per stage, partial sums joined with two shuffles;
 //   * the Riccati backward sweep (the dominant serial chain): every matrix entry of a stage's products is one work
 //     item -- P+ F (169 entries + 13 for tv), F'(P+ F) (182), the Q blocks (81), the rank-4 update of the cost-to-go (104)
 //     -- described by per-thread offset tables built once, so all threads run ONE instruction stream (no divergent
-//     formula branches); five CTA barriers per stage replace the ~110-instruction serial chains of the one-warp sweep;
+//     formula branches); five CTA barriers per stage replace the ~110-instruction serial chains of the one-warp sweep,
+//     and the back-substitution that only the rollout needs (the gains) runs on warp 0 beside the rank-4 update;
 //   * model evaluation (one stage per thread: a serial chain per stage, it does not get shorter), forward rollout and
 //     costates (short dependent chains over the stages) stay on warp 0 and reuse the one-warp code.
 //
@@ -24,7 +25,7 @@
 
 namespace nmpc {
 
-constexpr int GROUP_THREADS = 128;
+constexpr int GROUP_THREADS = 256;
 
 template <int N> struct GLayout {
     using L32 = Layout<float, N, false>;
@@ -38,8 +39,8 @@ template <int N> struct GLayout {
     static constexpr int Y = ZU + N * NZ;
     static constexpr int HDR = Y + N * NXI;
     static constexpr int BND = HDR + N * HDR_S;
-    static constexpr int RED = BND + 2 * NZ;            // CTA-reduction scratch: 4 warps x 8 values
-    static constexpr int R_FIXED = RED + 32;
+    static constexpr int RED = BND + 2 * NZ;            // CTA-reduction scratch: 8 warps x 8 values
+    static constexpr int R_FIXED = RED + 64;
     __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
     __host__ __device__ static constexpr int s_off(int) { return R_FIXED; }
     __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
@@ -361,53 +362,52 @@ template <int N> struct GroupSolver {
         for (int e = NXI + tid; e < N * NXI; e += NT) Y[e] += a * (double)DY[e];
     }
 
-    // ------------------------------------------------------------- Riccati backward, 128 threads ----
-    // Work items and their offset tables (all offsets relative to f32, the base of the fp32 region).
-    //   structured product  out = mA (j[oa] x0 + j[oa+sa] x1 + j[oa+2sa] x2) + mB (j[ob] x3 + j[ob+sb] x4 + j[ob+2sb] x5) + cc x[ic]
+    // ------------------------------------------------------------- Riccati backward, 256 threads ----
+    // Work items and their offset tables (offsets relative to f32, the base of the fp32 region; Jacobian words relative
+    // to the stage's 51-word block).
+    //   structured product  out = mA (j[a0] x0 + j[a1] x1 + j[a2] x2) + mB (j[b0] x3 + j[b1] x4 + j[b2] x5) + cc x[ic]
     //   with x = (xp, xv, xa): a row of P+ (phase A) or a column of P+ F / the vector tv (phase B); the output type
     //   (v-ordering w0 w1 w2 T p0 p1 p2 v0 v1 v2 r0 r1 r2) fixes the Jacobian words -- same formulas as Solver::ft_times.
-    struct SP { int oa, sa, ob, sb, ic, xoff, xs, dst; float mA, mB, cc; bool on; };
-    __device__ static SP sp_desc(int o)
+    struct SP { int ja[3], jb[3], x[6], xc, dst; float mA, mB, cc; bool on; };
+    __device__ static SP sp_desc(int o, int xoff, int xs, int dst, bool on)
     {
-        SP d{0, 0, 0, 0, 0, 0, 0, 0, 0.f, 0.f, 0.f, true};
-        if (o < 3) { d.mB = 1.f; d.ob = JVW + o; d.sb = 3; d.cc = (float)C::h; d.ic = 6 + o; }
-        else if (o == 3) { d.mA = 1.f; d.oa = JPT; d.sa = 1; d.mB = 1.f; d.ob = JVT; d.sb = 1; }
-        else if (o < 7) { d.cc = 1.f; d.ic = o - 4; }
-        else if (o < 10) { d.mA = 1.f; d.oa = JPV + o - 7; d.sa = 3; d.mB = 1.f; d.ob = JVV + o - 7; d.sb = 3; }
-        else { d.mA = 1.f; d.oa = JPR + o - 10; d.sa = 3; d.mB = 1.f; d.ob = JVR + o - 10; d.sb = 3; d.cc = 1.f; d.ic = 6 + o - 10; }
+        int oa = 0, sa = 0, ob = 0, sb = 0, ic = 0;
+        SP d;
+        d.mA = 0.f; d.mB = 0.f; d.cc = 0.f; d.on = on; d.dst = dst;
+        if (o < 3) { d.mB = 1.f; ob = JVW + o; sb = 3; d.cc = (float)C::h; ic = 6 + o; }
+        else if (o == 3) { d.mA = 1.f; oa = JPT; sa = 1; d.mB = 1.f; ob = JVT; sb = 1; }
+        else if (o < 7) { d.cc = 1.f; ic = o - 4; }
+        else if (o < 10) { d.mA = 1.f; oa = JPV + o - 7; sa = 3; d.mB = 1.f; ob = JVV + o - 7; sb = 3; }
+        else { d.mA = 1.f; oa = JPR + o - 10; sa = 3; d.mB = 1.f; ob = JVR + o - 10; sb = 3; d.cc = 1.f; ic = 6 + o - 10; }
+#pragma unroll
+        for (int q = 0; q < 3; q++) { d.ja[q] = oa + q * sa; d.jb[q] = ob + q * sb; }
+#pragma unroll
+        for (int q = 0; q < 6; q++) d.x[q] = xoff + q * xs;
+        d.xc = xoff + ic * xs;
         return d;
     }
-    __device__ __forceinline__ static float sp_eval(const SP& d, const float* __restrict__ jc, const float* __restrict__ x)
+    __device__ __forceinline__ float sp_eval(const SP& d, const float* __restrict__ jc) const
     {
-        const int s = d.xs;
-        const float a = (jc[d.oa] * x[0] + jc[d.oa + d.sa] * x[s]) + jc[d.oa + 2 * d.sa] * x[2 * s];
-        const float b = (jc[d.ob] * x[3 * s] + jc[d.ob + d.sb] * x[4 * s]) + jc[d.ob + 2 * d.sb] * x[5 * s];
-        return (d.mA * a + d.mB * b) + d.cc * x[d.ic * s];
+        const float a = (jc[d.ja[0]] * f32[d.x[0]] + jc[d.ja[1]] * f32[d.x[1]]) + jc[d.ja[2]] * f32[d.x[2]];
+        const float b = (jc[d.jb[0]] * f32[d.x[3]] + jc[d.jb[1]] * f32[d.x[4]]) + jc[d.jb[2]] * f32[d.x[5]];
+        return (d.mA * a + d.mB * b) + d.cc * f32[d.xc];
     }
 
     __device__ bool riccati_backward()
     {
         constexpr int PN = L32::PN, PF = L32::PF, TV = L32::TV, QUU = L32::QUU, QUR = L32::QUR, QV = L32::QV, QXI = L32::QXI,
                       YS = L32::YS, Y0 = L32::Y0, oGF = GL::SH_GF, oG = GL::SH_G, oPHI = GL::SH_PHID, oDY = GL::SH_DY, oD = GL::SH_D;
-        // ---- tables, two rounds of 128 work items each for phases A and B ----
-        SP pa[2], pb[2];
-        int tvrow[2];
-#pragma unroll
-        for (int rd = 0; rd < 2; rd++) {
-            const int w = tid + NT * rd;
-            // phase A: w < 169 -> PF[r][o] from row r of P+;  169 <= w < 182 -> tv[w - 169]
-            pa[rd] = sp_desc(w < 169 ? w % 13 : 0);
-            pa[rd].on = w < 169;
-            pa[rd].xoff = PN + (w < 169 ? w / 13 : 0) * 13; pa[rd].xs = 1; pa[rd].dst = PF + (w < 169 ? w : 0);
-            tvrow[rd] = (w >= 169 && w < 182) ? w - 169 : -1;
-            // phase B: w < 182 -> GF[o][j] from column j of P+ F (j < 13) or from tv (j = 13)
-            const int j = w / 13, o = w % 13;
-            pb[rd] = sp_desc(w < 182 ? o : 0);
-            pb[rd].on = w < 182;
-            pb[rd].xoff = (w < 182 && j == 13) ? TV : PF + (w < 182 ? j : 0);
-            pb[rd].xs = (w < 182 && j == 13) ? 1 : 13;
-            pb[rd].dst = oGF + (w < 182 ? o * 14 + j : 0);
-        }
+        static_assert(NT >= 32 + 182 && NT >= 32 + 104, "work items of a phase must fit one round");
+        // phase A on warps 1.. (warp 0 may still be finishing the previous stage's back-substitution):
+        //   w < 169 -> PF[r][o] from row r of P+;  169 <= w < 182 -> tv[w - 169]
+        const int wA = tid - 32;
+        const bool onA = wA >= 0 && wA < 169;
+        const SP pa = sp_desc(onA ? wA % 13 : 0, PN + (onA ? wA / 13 : 0) * 13, 1, PF + (onA ? wA : 0), onA);
+        const int tvrow = (wA >= 169 && wA < 182) ? wA - 169 : -1;
+        // phase B on all warps: w < 182 -> GF[o][j] from column j of P+ F (j < 13) or from tv (j = 13)
+        const bool onB = tid < 182;
+        const int jB = onB ? tid / 13 : 0, oB = onB ? tid % 13 : 0;
+        const SP pb = sp_desc(oB, jB == 13 ? TV : PF + jB, jB == 13 ? 1 : 13, oGF + oB * 14 + jB, onB);
         // phase B2: the Q blocks as gather-sums of at most five terms (81 work items)
         GTerm b2[5];
         int b2dst = -1;
@@ -445,18 +445,19 @@ template <int N> struct GroupSolver {
                 b2dst = QXI + w - 4;
             }
         }
-        // phase D: 91 entries of P_k (i >= j) + 13 of p_k
+        // phase D on warps 1..: 91 entries of P_k (i >= j) + 13 of p_k
+        const int wD = tid - 32;
         int di = 0, dj = 0, dgf = -1, dphi = -1;
-        const bool dmat = tid < 91, dvec = tid >= 91 && tid < 104;
+        const bool dmat = wD >= 0 && wD < 91, dvec = wD >= 91 && wD < 104;
         if (dmat) {
-            int i = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-            i += ((i + 1) * (i + 2) / 2 <= tid) - (i * (i + 1) / 2 > tid);
-            const int j = tid - i * (i + 1) / 2;
+            int i = (int)((sqrtf(8.0f * (float)wD + 1.0f) - 1.0f) * 0.5f);
+            i += ((i + 1) * (i + 2) / 2 <= wD) - (i * (i + 1) / 2 > wD);
+            const int j = wD - i * (i + 1) / 2;
             di = i; dj = j;
             dgf = (i < 9) ? oGF + (4 + i) * 14 + 4 + j : -1;
             dphi = (i < 9) ? (i == j ? 8 + i : (i < 3 ? 17 + i + j - 1 : -1)) : (i == j ? 4 + i - 9 : -1);
         } else if (dvec) {
-            di = tid - 91;
+            di = wD - 91;
         }
         // the terminal stage is the generic stage with P+ = 0: no products, the Q blocks come out of zeros
         for (int e = tid; e < 169; e += NT) { f32[PN + e] = 0.f; f32[PF + e] = 0.f; }
@@ -468,27 +469,22 @@ template <int N> struct GroupSolver {
             if (k < N - 1) {
                 const float* jc = JC + k * NJC;
                 // ---- phase A ----
+                if (pa.on) f32[pa.dst] = sp_eval(pa, jc);
+                if (tvrow >= 0) {
+                    const float* pr = f32 + PN + tvrow * 13;
+                    const float* dk = f32 + oD + k * NXI;
+                    float c0 = f32[oDY + (k + 1) * NXI + tvrow], c1 = 0.f, c2 = 0.f;
 #pragma unroll
-                for (int rd = 0; rd < 2; rd++) {
-                    if (pa[rd].on) f32[pa[rd].dst] = sp_eval(pa[rd], jc, f32 + pa[rd].xoff);
-                    if (tvrow[rd] >= 0) {
-                        const float* pr = f32 + PN + tvrow[rd] * 13;
-                        const float* dk = f32 + oD + k * NXI;
-                        float c0 = f32[oDY + (k + 1) * NXI + tvrow[rd]], c1 = 0.f, c2 = 0.f;
-#pragma unroll
-                        for (int q = 0; q < 13; q += 3) {
-                            c0 += pr[q] * dk[q];
-                            if (q + 1 < 13) c1 += pr[q + 1] * dk[q + 1];
-                            if (q + 2 < 13) c2 += pr[q + 2] * dk[q + 2];
-                        }
-                        f32[TV + tvrow[rd]] = (c0 + c1) + c2;
+                    for (int q = 0; q < 13; q += 3) {
+                        c0 += pr[q] * dk[q];
+                        if (q + 1 < 13) c1 += pr[q + 1] * dk[q + 1];
+                        if (q + 2 < 13) c2 += pr[q + 2] * dk[q + 2];
                     }
+                    f32[TV + tvrow] = (c0 + c1) + c2;
                 }
                 __syncthreads();
                 // ---- phase B ----
-#pragma unroll
-                for (int rd = 0; rd < 2; rd++)
-                    if (pb[rd].on) f32[pb[rd].dst] = sp_eval(pb[rd], jc, f32 + pb[rd].xoff);
+                if (pb.on) f32[pb.dst] = sp_eval(pb, jc);
                 __syncthreads();
             }
             // ---- phase B2: Q blocks ----
@@ -499,14 +495,14 @@ template <int N> struct GroupSolver {
                 f32[b2dst] = v;
             }
             __syncthreads();
-            // ---- phase C (warp 0): pivot block factorised redundantly in registers, 13 + 1 columns solved ----
+            // ---- phase C1 (warp 0): pivot block factorised redundantly in registers, forward substitution of 13 + 1 columns ----
+            float l[10], li[4], x[4];
             if (warp == 0) {
-                float l[10], li[4], a[16];
+                float a[16];
                 a[0] = f32[QUU + 0]; a[4] = f32[QUU + 4]; a[5] = f32[QUU + 5]; a[8] = f32[QUU + 8]; a[9] = f32[QUU + 9]; a[10] = f32[QUU + 10];
                 a[12] = f32[QUU + 12]; a[13] = f32[QUU + 13]; a[14] = f32[QUU + 14]; a[15] = f32[QUU + 15];
                 ok &= chol4<float>(a, l, li);
                 if (lane < 14) {
-                    float x[4];
 #pragma unroll
                     for (int r = 0; r < 4; r++) x[r] = (lane < 13) ? f32[QUR + r * 13 + lane] : f32[QV + r];
                     fsub4<float>(l, li, x);
@@ -514,15 +510,20 @@ template <int N> struct GroupSolver {
                     const int ystr = (lane < 13) ? 13 : 1;
 #pragma unroll
                     for (int r = 0; r < 4; r++) ys[r * ystr] = x[r];
-                    bsub4<float>(l, li, x);
-                    float* kg = (lane < 13) ? sw.KG + k * 52 + lane : sw.KFF + k * 4;
-#pragma unroll
-                    for (int r = 0; r < 4; r++) kg[r * ystr] = -x[r];
                 }
             }
             __syncthreads();
-            // ---- phase D: P_k = blkdiag(Q_xx, Phi_qq) - Y'Y,  p_k = q_xi - Y' y0 ----
-            if (dmat) {
+            // ---- phase C2 (warp 0: back-substitution -> gains, needed only by the rollout)  ||  phase D (warps 1..):
+            //      P_k = blkdiag(Q_xx, Phi_qq) - Y'Y,  p_k = q_xi - Y' y0 ----
+            if (warp == 0) {
+                if (lane < 14) {
+                    bsub4<float>(l, li, x);
+                    float* kg = (lane < 13) ? sw.KG + k * 52 + lane : sw.KFF + k * 4;
+                    const int ystr = (lane < 13) ? 13 : 1;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) kg[r * ystr] = -x[r];
+                }
+            } else if (dmat) {
                 float v = (dgf >= 0) ? f32[dgf] : 0.f;
                 if (dphi >= 0) v += f32[oPHI + k * GL::PHI_S + dphi];
                 const float* ys = f32 + YS;
@@ -542,7 +543,7 @@ template <int N> struct GroupSolver {
 };
 
 // =====================================================================================
-// the kernel: grid = B CTAs of 128 threads; dynamic smem = GLayout::bytes(mcap)
+// the kernel: grid = B CTAs of 256 threads; dynamic smem = GLayout::bytes(mcap)
 // =====================================================================================
 template <int N>
 __global__ void __launch_bounds__(GROUP_THREADS) nmpc_ipm_group_kernel(const MixedParams prm)

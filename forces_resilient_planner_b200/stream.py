@@ -44,8 +44,17 @@ class RecedingHorizonStream:
         self.poly_m = t(batch.nrows[:, 1:2], np.int32); self.poly_idx = t(np.zeros((self.B, self.N)), np.int32)
         self.ellipsoid = t(np.tile(np.diag(W.EGO_E).reshape(1, 1, 9), (self.B, self.N, 1)))
         self.weights = (7.0, 1.0, 80.0, 12.0, 0.5)
-        # dynamic inputs of a replan (host-generated, uploaded each cycle)
-        self.ref_pos = t(batch.hdr[:, :, 0:3]); self.ref_yaw = t(batch.hdr[:, :, 9]); self.ext_acc = t(batch.hdr[:, 0, 3:6])
+        # dynamic inputs of a replan (host-generated): ONE pinned staging buffer, ONE H2D copy per cycle, three views
+        n0, n1, n2 = self.B * self.N * 3, self.B * self.N, self.B * 3
+        self.h_in = torch.empty(n0 + n1 + n2, dtype=torch.float64).pin_memory()
+        self.d_in = torch.empty(n0 + n1 + n2, dtype=torch.float64, device=self.dev)
+        self.ref_pos = self.d_in[0:n0].view(self.B, self.N, 3); self.ref_yaw = self.d_in[n0:n0 + n1].view(self.B, self.N)
+        self.ext_acc = self.d_in[n0 + n1:].view(self.B, 3)
+        self._h_views = (self.h_in[0:n0].view(self.B, self.N, 3).numpy(), self.h_in[n0:n0 + n1].view(self.B, self.N).numpy(),
+                         self.h_in[n0 + n1:].view(self.B, 3).numpy())
+        # results a replan hands back to the host: first commands and (flag, iterations, ...), pinned
+        self.h_cmd = torch.empty((self.B, 4), dtype=torch.float64).pin_memory()
+        self.h_ii = torch.empty((self.B, 4), dtype=torch.int32).pin_memory()
         # solver state on the device
         self.xinit = t(batch.xinit); self.z0 = t(batch.z0); self.z = torch.empty_like(self.z0)
         self.zprev = self.z0.clone()      # the plan in force (mpc_output_): only ACCEPTED solves ever enter it
@@ -78,10 +87,11 @@ class RecedingHorizonStream:
         # 36.4 KB of shared memory per agent -> 1184 instead of 888 resident agents per GPU, so a 1024-agent fleet is ONE
         # wave, and every iteration is shorter); its fp64 re-solve of an agent it gives up on rides on the same stream
         self.mixed = mixed
-        # the warp-group kernel (nmpc_solve_batch_lowlatency_f64: 128 threads per agent, ~0.7x the time per iteration)
-        # pays when the fleet leaves most of the GPU idle; default: on for mixed streams of at most 2 agents per SM
+        # the warp-group kernel (nmpc_solve_batch_lowlatency_f64: 256 threads per agent, one agent per SM, ~0.65x the time
+        # per iteration) pays when the fleet leaves most of the GPU idle; default: on for mixed streams of at most one
+        # agent per SM (a second wave would cost more than the shorter iterations save)
         if lowlatency is None:
-            lowlatency = mixed and self.B <= 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count
+            lowlatency = mixed and self.B <= torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.lowlatency = bool(lowlatency)
         self.order = torch.arange(self.B, dtype=torch.int32, device=self.dev)
         self.cycle = 0
@@ -89,6 +99,8 @@ class RecedingHorizonStream:
     # -- the three launches of a replan, all on `stream` ---------------------------------------------
     def _enqueue(self, stream, warm: bool):
         torch = self.torch
+        with torch.cuda.stream(stream):
+            self.d_in.copy_(self.h_in, non_blocking=True)          # this cycle's references and f_ext
         if warm:
             # result handling of the previous cycle, per agent: accepted plans are adopted, a failed solve (whose
             # output may be NaN) leaves nothing behind -- that agent restarts from the cold guess at its state
@@ -122,6 +134,9 @@ class RecedingHorizonStream:
             fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(_lib.NmpcOpts)] + \
                 [ctypes.c_void_p] * 5
             _check(fn(*args, order, ctypes.c_void_p(stream.cuda_stream)))
+        with torch.cuda.stream(stream):                             # what the host reads back: commands, flags, iterations
+            self.h_cmd.copy_(self.z[:, 0, 0:4], non_blocking=True)
+            self.h_ii.copy_(self.info_int, non_blocking=True)
 
     def replan(self, ref_pos: np.ndarray, ref_yaw: np.ndarray, ext_acc: np.ndarray):
         """One cycle.  Host arrays in (refs of this cycle), host arrays out (first command, flags).
@@ -131,9 +146,7 @@ class RecedingHorizonStream:
         (capture does not execute) and every later cycle replays it."""
         torch = self.torch
         st = torch.cuda.current_stream(self.dev)
-        self.ref_pos.copy_(torch.from_numpy(ref_pos), non_blocking=True)
-        self.ref_yaw.copy_(torch.from_numpy(ref_yaw), non_blocking=True)
-        self.ext_acc.copy_(torch.from_numpy(ext_acc), non_blocking=True)
+        self._h_views[0][...] = ref_pos; self._h_views[1][...] = ref_yaw; self._h_views[2][...] = ext_acc
         if self.cycle == 0:
             self._enqueue(st, warm=False)
         elif self.cycle == 1 or not self.use_graph:
@@ -147,10 +160,9 @@ class RecedingHorizonStream:
                     self._enqueue(torch.cuda.current_stream(self.dev), warm=True)
             self.graph.replay()
         self.cycle += 1
-        cmd = self.z[:, 0, 0:4].cpu().numpy()            # D2H read of the step's result (synchronises)
-        flag = self.info_int[:, 0].cpu().numpy()
-        it = self.info_int[:, 1].cpu().numpy()
-        return cmd, flag, it
+        st.synchronize()                                  # the step's results are in the pinned buffers now
+        ii = self.h_ii.numpy()
+        return self.h_cmd.numpy().copy(), ii[:, 0].copy(), ii[:, 1].copy()
 
 def synthetic_refs(batch: W.Batch, step: int, rng: np.random.Generator, ext_acc: np.ndarray, period: int = 20):
     """References of replan `step` for the config-2 style scenario: the straight-line reference

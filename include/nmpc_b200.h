@@ -116,7 +116,7 @@ int nmpc_solve_batch_mixed_f64(int B, int N, int mcap, const double *xinit, cons
                                const int *order, void *cuda_stream);
 
 /* Low-latency variant of nmpc_solve_batch_mixed_f64 (same arguments, same algorithm, tolerances and exit codes): one
- * warp-GROUP (128 threads) per problem instead of one warp (csrc/nmpc_ipm_group.cuh).  For small fleets -- fewer
+ * warp-GROUP (256 threads) per problem instead of one warp (csrc/nmpc_ipm_group.cuh).  For small fleets -- fewer
  * problems than the GPU has SMs x a few, e.g. BASELINE config 5 at 128 agents per GPU -- where the latency of one
  * solve, not the throughput of thousands, is what the caller waits for: an interior-point iteration takes about half
  * the time of the one-warp kernels'.  With thousands of problems the one-warp kernels are the faster choice.      */

@@ -470,7 +470,7 @@ def test_rank_longest_first_equals_stable_argsort():
         assert np.array_equal(got, want), B
 
 
-@pytest.mark.parametrize("B,expect_group", [(40, True), (400, False)])
+@pytest.mark.parametrize("B,expect_group", [(40, True), (200, False)])
 def test_mixed_precision_stream_follows_the_fp64_closed_loop(B, expect_group):
     """The receding-horizon stream through the mixed-precision kernels (warp-group kernel for a small fleet, one-warp
     kernel for a large one) against the same stream through the fp64 kernel: every replan converges, the commands agree
