@@ -159,7 +159,7 @@ template <typename T> __device__ __forceinline__ T warp_min(T v)
     return v;
 }
 template <typename T> struct Eps;
-template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int logvars = 4, logrows = 8; };
+template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int logvars = 8, logrows = 8; };
 template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f; static constexpr int logvars = 1, logrows = 2; };
 
 __device__ __forceinline__ int e_col(int i) { return i < 9 ? 8 + i : i - 5; }   // xi index -> z index
@@ -204,8 +204,28 @@ __device__ __forceinline__ void tma_store(void* dst, const void* src, uint32_t b
 // in-register Cholesky of a 4x4 SPD matrix given row-major a[16] (lower triangle used); L (10 values)
 // as l[10] = {l00, l10,l11, l20,l21,l22, l30,l31,l32,l33}, li[4] = 1/diag (no divisions anywhere:
 // 1/sqrt(d) comes from rsqrt); returns false on a non-positive pivot.
-__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+// 1/sqrt(x) in double precision from the single-precision SFU seed and two Newton steps (relative error 2^-22 -> 2^-43 ->
+// rounding level): 12 instructions on the critical path of every pivot instead of the ~30 of the library routine.
+// The pivots of the 4x4 blocks (1e-3 .. 1e12) are far inside the single-precision exponent range.
+__device__ __forceinline__ double rsqrt_t(double x)
+{
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);
+    y = y * (1.5 - hx * y * y);
+    return y;
+}
 __device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+// 1/x for the slacks of the barrier terms (1e-10 .. 1e2): single-precision SFU seed + two Newton steps, 9 instructions
+// instead of the ~28 of an IEEE double division; error at rounding level (the seed's 2^-23 squared twice)
+__device__ __forceinline__ double rcp_t(double x)
+{
+    double r = (double)__frcp_rn((float)x);
+    r = r * (2.0 - x * r);
+    r = r * (2.0 - x * r);
+    return r;
+}
+__device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
 template <typename T> __device__ __forceinline__ bool chol4(const T* a, T l[10], T li[4])
 {
     bool ok = true;
@@ -429,7 +449,7 @@ template <typename T, int N, bool PC = false> struct Solver {
             T* phi = PHID + k * L::PHI_S;
             if (e < 8 || e >= NZ) {
                 const T zi = Z[e];
-                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                const T isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
                 phi[i] = cost_hess_diag<T>(i, HDR + k * L::HDR_S, k == 0, final_variant && k == N - 1) + ZL[e] * isl + ZU[e] * isu;
                 G[e] += mu_t * (isu - isl);
             } else {
@@ -444,7 +464,7 @@ template <typename T, int N, bool PC = false> struct Solver {
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 T r[4]; load_row(k, j, r);
-                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
+                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = rcp_t(sj);
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T sg = lj * is, tt = (mu_t + lj * rc) * is;
                 d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
@@ -629,20 +649,20 @@ template <typename T, int N, bool PC = false> struct Solver {
             __syncwarp();
             // ---- phase D ------------------------------------------------------------------------
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int e = lane + 32 * t;
-                if (t < 3 && e < 91) {
+            for (int t = 0; t < 3; t++) {
+                if (lane + 32 * t < 91) {
                     const int i = ti[t], j = tj[t];                // xi-ordering (x0..8, q0..3), i >= j
                     T v = (nx && goff[t] >= 0) ? GG[goff[t]] : T(0);
                     if (poff[t] >= 0) v += phi[poff[t]];
                     v -= (YS[i] * YS[j] + YS[13 + i] * YS[13 + j]) + (YS[26 + i] * YS[26 + j] + YS[39 + i] * YS[39 + j]);
                     PN[i * 13 + j] = v;
                     PN[j * 13 + i] = v;
-                } else if (e >= 91 && e < 104) {
-                    const int i = e - 91;
-                    const T qxi = (i < 9) ? QXI[i] : gk[i - 5];    // the u_prev rows of q~ are the stage gradient itself
-                    P[k * NXI + i] = qxi - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
                 }
+            }
+            if (lane < NXI) {                                      // p_k, one entry per lane
+                const int i = lane;
+                const T qxi = (i < 9) ? QXI[i] : gk[i - 5];        // the u_prev rows of q~ are the stage gradient itself
+                P[k * NXI + i] = qxi - ((YS[i] * Y0[0] + YS[13 + i] * Y0[1]) + (YS[26 + i] * Y0[2] + YS[39 + i] * Y0[3]));
             }
             __syncwarp();
             if (fac_out) {   // factor of stage k: P_k (91 words, PSYM layout) -> P region; [K_k 52 | Quu^-1 packed lower 10 | J_k 51] -> KQJ region
@@ -852,7 +872,7 @@ template <typename T, int N, bool PC = false> struct Solver {
             if (e < 8 || e >= NZ) {
                 const int i = e % NZ;
                 const T zi = Z[e], zl = ZL[e], zu = ZU[e], dzi = dza[t];
-                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                const T isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
                 const T cl = -zl * dzi * (dzi * isl + T(1)), cu = -zu * dzi * (dzi * isu - T(1));
                 dg = (mu_t - cu) * isu - (mu_t - cl) * isl;
             }
@@ -865,7 +885,7 @@ template <typename T, int N, bool PC = false> struct Solver {
             T g0 = T(0), g1 = T(0), g2 = T(0);
             for (int j = 0; j < m; j++) {
                 T r[4]; load_row(k, j, r);
-                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = T(1) / sj;
+                const T sj = S[k * SS + j], lj = LC[k * SS + j], is = rcp_t(sj);
                 const T rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const T ds = -rc - (r[0] * DZAP[k * 3] + r[1] * DZAP[k * 3 + 1] + r[2] * DZAP[k * 3 + 2]);
                 const T cr = -lj * ds * (ds * is + T(1));
@@ -985,12 +1005,12 @@ template <typename T, int N, bool PC = false> struct Solver {
                 const T ds = -rc - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
                 T dl;
                 if (PC) {
-                    const T is = T(1) / sj;
+                    const T is = rcp_t(sj);
                     const T dsa = -rc - (r[0] * DZAP[k * 3] + r[1] * DZAP[k * 3 + 1] + r[2] * DZAP[k * 3 + 2]);
                     const T cr = -lj * dsa * (dsa * is + T(1));
                     dl = (mu_t - cr - lj * ds) * is - lj;
                 } else {
-                    dl = (mu_t - lj * ds) / sj - lj;
+                    dl = (mu_t - lj * ds) * rcp_t(sj) - lj;
                 }
                 S[k * SS + j] = sj + a * ds;
                 LC[k * SS + j] = lj + ad * dl;
@@ -1003,7 +1023,7 @@ template <typename T, int N, bool PC = false> struct Solver {
             if (e < 8 || e >= NZ) {
                 const int i = e % NZ;
                 const T zl = ZL[e], zu = ZU[e];
-                const T isl = T(1) / (zi - BND[i]), isu = T(1) / (BND[NZ + i] - zi);
+                const T isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
                 T cl = T(0), cu = T(0);
                 if (PC) {
                     const T da = dza[t];

@@ -177,7 +177,7 @@ template <int N> struct GroupSolver {
                 double sl = zk[i] - lower_bound<double>(i), su = upper_bound<double>(i) - zk[i];
                 if (i >= 8 && k == 0) { sl = 1.0; su = 1.0; }
                 prod *= sl * su;
-                if (i % 4 == 3 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
+                if (i % 8 == 7 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
             }
             const int m = live(k);
             double al0 = 0.0, al1 = 0.0, al2 = 0.0;
@@ -254,7 +254,7 @@ template <int N> struct GroupSolver {
             float* phi = PHID + k * GL::PHI_S;
             if (e < 8 || e >= NZ) {
                 const double zi = Z[e], zl = ZL[e], zu = ZU[e];
-                const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
+                const double isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
                 phi[i] = (float)(cost_hess_diag<double>(i, HDR + k * GL::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu);
                 G[e] = (float)((double)G[e] + ((zl - mu_t * isl) - (zu - mu_t * isu)));
             } else {
@@ -270,7 +270,7 @@ template <int N> struct GroupSolver {
                 const int m = live(k);
                 for (int j = tid % RP; j < m; j += RP) {
                     double r[4]; load_row(k, j, r);
-                    const double sj = S[k * SS + j], lj = LC[k * SS + j], is = 1.0 / sj;
+                    const double sj = S[k * SS + j], lj = LC[k * SS + j], is = rcp_t(sj);
                     const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                     const double sg = lj * is, tt = (mu_t + lj * (rc - sj)) * is;
                     acc[0] += r[0] * r[0] * sg; acc[1] += r[1] * r[1] * sg; acc[2] += r[2] * r[2] * sg;
@@ -339,13 +339,13 @@ template <int N> struct GroupSolver {
     {
         for_rows([&](int k, int j, const double (&r)[4], double sj, double lj, double rc) {
             const double ds = -rc - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
-            LC[k * SS + j] = lj + ad * ((mu_t - lj * ds) / sj - lj);
+            LC[k * SS + j] = lj + ad * ((mu_t - lj * ds) * rcp_t(sj) - lj);
         });
         for (int e = tid; e < N * NZ; e += NT) {
             if (!(e < 8 || e >= NZ)) continue;
             const int i = e % NZ;
             const double zi = Z[e], dzi = (double)DZ[e], zl = ZL[e], zu = ZU[e];
-            const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
+            const double isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
             ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
             ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
         }

@@ -195,7 +195,7 @@ template <int N> struct MixedSolver {
                 double sl = zk[i] - lower_bound<double>(i), su = upper_bound<double>(i) - zk[i];
                 if (i >= 8 && k == 0) { sl = 1.0; su = 1.0; }
                 prod *= sl * su;
-                if (i % 4 == 3 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
+                if (i % 8 == 7 || i == NZ - 1) { ls += log(prod); prod = 1.0; }     // <= 16 slacks per product: no underflow
             }
             const int m = live(k);
             double al0 = 0.0, al1 = 0.0, al2 = 0.0;
@@ -263,7 +263,7 @@ template <int N> struct MixedSolver {
             float* phi = PHID + k * ML::PHI_S;
             if (e < 8 || e >= NZ) {
                 const double zi = Z[e], zl = ZL[e], zu = ZU[e];
-                const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
+                const double isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
                 phi[i] = (float)(cost_hess_diag<double>(i, HDR + k * ML::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu);
                 G[e] = (float)((double)G[e] + ((zl - mu_t * isl) - (zu - mu_t * isu)));
             } else {
@@ -278,7 +278,7 @@ template <int N> struct MixedSolver {
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 double r[4]; load_row(k, j, r);
-                const double sj = S[k * SS + j], lj = LC[k * SS + j], is = 1.0 / sj;
+                const double sj = S[k * SS + j], lj = LC[k * SS + j], is = rcp_t(sj);
                 const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const double sg = lj * is, tt = (mu_t + lj * (rc - sj)) * is;
                 d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
@@ -342,14 +342,14 @@ template <int N> struct MixedSolver {
                 const double sj = S[k * SS + j], lj = LC[k * SS + j];
                 const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
                 const double ds = -rc - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
-                LC[k * SS + j] = lj + ad * ((mu_t - lj * ds) / sj - lj);
+                LC[k * SS + j] = lj + ad * ((mu_t - lj * ds) * rcp_t(sj) - lj);
             }
         }
         for (int e = lane; e < N * NZ; e += 32) {
             if (!(e < 8 || e >= NZ)) continue;
             const int i = e % NZ;
             const double zi = Z[e], dzi = (double)DZ[e], zl = ZL[e], zu = ZU[e];
-            const double isl = 1.0 / (zi - BND[i]), isu = 1.0 / (BND[NZ + i] - zi);
+            const double isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
             ZL[e] = zl + ad * ((mu_t - zl * dzi) * isl - zl);
             ZU[e] = zu + ad * ((mu_t + zu * dzi) * isu - zu);
         }
