@@ -151,7 +151,8 @@ int check_solve_args(int B, int N, int mcap, const void* xinit, const void* z0, 
 int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
                  const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int,
                  void* info_real, void* stream, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
-                 void* lc_out = nullptr, const int* order = nullptr, const int* count = nullptr, int io32 = 0)
+                 void* lc_out = nullptr, const int* order = nullptr, const int* count = nullptr, int io32 = 0,
+                 const void* z_warm = nullptr)
 {
     nmpc_opts o;
     if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
@@ -159,6 +160,7 @@ int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, cons
     nmpc::Params<double> prm;
     prm.B = B; prm.mcap = mcap; prm.variant = variant; prm.io32 = io32;
     prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order; prm.count = count;
+    prm.z_warm = z_warm;
     prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
     std::memcpy(&prm.o, &o, sizeof(o));
@@ -198,7 +200,7 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
     nmpc_opts o64 = o;
     o64.pc = 0;
     int rc = solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, &o64, z_out, info_int, info_real, stream,
-                          y_out, zl_out, zu_out, lc_out, ws + 4, ws, io32);
+                          y_out, zl_out, zu_out, lc_out, ws + 4, ws, io32, /*z_warm = the mixed kernel's last iterates*/ z_out);
     CUDA_TRY(cudaFreeAsync(ws, st));
     return rc;
 }

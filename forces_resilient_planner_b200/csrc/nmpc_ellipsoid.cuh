@@ -21,8 +21,13 @@
 // does out of shared memory.  oracle/ellipsoid_np.py restates the reference literally
 // (Schur/Sylvester, Pade); the two agree to ~1e-13 relative.
 //
-// One deliberate deviation, in both: the reference accumulates `temp += sqrt(X.trace())` into an
-// uninitialised double (:573, :597 -- undefined behaviour); here temp starts at 0.
+// Two deliberate deviations, in both (each a latent bug of the reference, restated as what the formula means):
+//   1. the reference accumulates `temp += sqrt(X.trace())` into an uninitialised double (:573, :597 -- undefined
+//      behaviour); here temp starts at 0;
+//   2. updateMatrix never ASSIGNS At_(5,8) -- the thrust term of d(acc_z)/d(yaw) is zero, so there is no `At_(5,8) = ...`
+//      line next to :643-644 -- it only does `At_(5,8) += ...` (:689) on the class member At_, so in the reference that
+//      entry keeps growing over all 20 stages of a replan and over every replan; here the linearisation of a stage is
+//      built from zero (the drag term alone), as for every other entry.
 //
 // The stages are a recurrence (Q_init and Q2 carry over), so a warp walks its agent's horizon with the lanes
 // splitting the matrix entries; what does not take part in the recurrence is done for all stages at

@@ -50,6 +50,8 @@ template <typename T> struct Params {
     const int* nrows;  // [B][N]
     const int* order;  // [B] or nullptr: CTA i solves problem order[i] (launch order = scheduling order)
     const int* count;  // nullptr, or device counter: only the first *count entries of `order` are live
+    const void* z_warm;   // re-solve only (count != nullptr): the mixed-precision kernel's last iterate [B][N][17]; a problem it
+                          // gave up on for a factorisation breakdown (-5) or at its iteration cap (0) restarts from there
     void* z_out;          // [B][N][17]
     int* info_int;     // [B][4]  exitflag, iterations, backtracks, 1 if this is a re-solve (count != nullptr)
     void* info_real;      // [B][8]  res_eq res_ineq rsnorm rcompnorm pobj mu alpha_p alpha_d
@@ -1054,6 +1056,10 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     const int mcap = prm.mcap;
     const bool io32 = sizeof(T) == 8 && prm.io32 != 0;
     const size_t esz = io32 ? 4 : sizeof(T);
+    // re-solve of a problem the mixed-precision kernel left at -5 / 0: its last iterate is close to the solution
+    // (single precision breaks down late, when the barrier terms are large), so start there with a small barrier
+    const bool warm = prm.count && prm.z_warm && (prm.info_int[(size_t)b * 4] == -5 || prm.info_int[(size_t)b * 4] == 0);
+    const void* z_src = warm ? prm.z_warm : prm.z0;
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* nr = reinterpret_cast<int*>(smem_raw + 16);
@@ -1073,7 +1079,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, bytes_z + bytes_h + bytes_n);
-        tma_load(io32 ? stg_z : s.Z, static_cast<const unsigned char*>(prm.z0) + (size_t)b * N * NZ * esz, bytes_z, bar);
+        tma_load(io32 ? stg_z : s.Z, static_cast<const unsigned char*>(z_src) + (size_t)b * N * NZ * esz, bytes_z, bar);
         tma_load(stg + L::STG_HDR, static_cast<const unsigned char*>(prm.hdr) + (size_t)b * N * 10 * esz, bytes_h, bar);
         tma_load(nr, prm.nrows + (size_t)b * N, bytes_n, bar);
     }
@@ -1089,6 +1095,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     __syncwarp();
 
     // ---- initial point -------------------------------------------------------------------
+    const T mu0 = warm ? (T)fmin(o.mu0, 0.1) : (T)o.mu0;
     if (lane < NZ) { s.BND[lane] = lower_bound<T>(lane); s.BND[NZ + lane] = upper_bound<T>(lane); }
     for (int e = lane; e < N * NZ; e += 32) s.DZ[e] = T(0);      // staging area is dead now; evaluate(0) reads 0 * dz
     int ncomp = 0;
@@ -1103,8 +1110,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
                 const T pl = fmin(kp * fmax(T(1), fabs(lb)), kp * (ub - lb));
                 const T pu = fmin(kp * fmax(T(1), fabs(ub)), kp * (ub - lb));
                 v = fmin(fmax(v, lb + pl), ub - pu);
-                s.ZL[k * NZ + i] = (T)o.mu0 / (v - lb);
-                s.ZU[k * NZ + i] = (T)o.mu0 / (ub - v);
+                s.ZL[k * NZ + i] = mu0 / (v - lb);
+                s.ZU[k * NZ + i] = mu0 / (ub - v);
                 ncomp += 2;
             } else {
                 s.ZL[k * NZ + i] = T(0);
@@ -1120,7 +1127,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
             T sl = (r[3] + C::hu) - (r[0] * s.Z[k * NZ + 8] + r[1] * s.Z[k * NZ + 9] + r[2] * s.Z[k * NZ + 10]);
             sl = fmax(sl, (T)o.s_floor);
             s.S[k * s.SS + j] = sl;
-            s.LC[k * s.SS + j] = (T)o.mu0 / sl;
+            s.LC[k * s.SS + j] = mu0 / sl;
             ncomp++;
         }
     }

@@ -225,75 +225,86 @@ template <int N> struct MixedSolver {
         f_out = warp_sum(f); th_out = warp_sum(th); ls_out = warp_sum(ls); req_out = warp_max(rq); rs_out = warp_max(rs);
     }
 
-    // ---------------------------------------- inequality residual, complementarity, mu ------
-    __device__ void residuals(double& rin_n, double& rcomp, double& csum, double& cmin)
+    // ------------------- accept the primal step, measure the new point, assemble the next Newton system ------
+    // One pass over the corridor rows and one over the (stage, variable) pairs does what used to be three phases:
+    //   * the accepted primal step: s += a ds, z += a dz, y += a dy (the multipliers were stepped before the line search);
+    //   * the residuals of the NEW point that are not evaluate()'s: inequality residual (the rows are linear: the
+    //     residual shrinks by 1 - a), complementarity products, their sum / max / min;
+    //   * the barrier-augmented stage Hessians, and the right-hand side in a form that does not need the barrier target
+    //     yet:   rhs = [r + (z_l - z_u) + A' lambda (r_c - s)/s]  +  mu_t [1/s_u - 1/s_l + A'(1/s)]  =  G + mu_t * T.
+    //     (mu_t follows from the complementarity sum this very pass produces.)  T is parked in the dead step array DZ,
+    //     the rows' partial sums in the dead dy array; finish_rhs(mu_t) adds mu_t * T afterwards.
+    // Both brackets are large and cancel only along directions whose Hessian entry (z/s, lambda/s) is larger still, so
+    // rounding them separately to single precision moves the step by far less than the stopping tolerance.
+    // a = 0 with dz = dy = 0 is the initial point.
+    __device__ void post_step(double a, double& rin_n, double& rcomp, double& csum, double& cmin)
     {
         double rin = 0.0, cmx = 0.0, cs = 0.0, cmn = 1e30;
+        for (int e = NXI + lane; e < N * NXI; e += 32) Y[e] += a * (double)DY[e];
+        __syncwarp();                                          // dy is dead from here: rows park their sums in it
         for (int k = lane; k < N; k += 32) {
+            float* phi = PHID + k * ML::PHI_S;
+            float* tmp = DY + k * NXI;                         // d0 d1 d2 | t0 t1 t2 (coefficient of mu_t) | g0 g1 g2
+            double o01 = 0.0, o02 = 0.0, o12 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
             const int m = live(k);
             for (int j = 0; j < m; j++) {
                 double r[4]; load_row(k, j, r);
-                const double sj = S[k * SS + j], lj = LC[k * SS + j];
-                const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                const double so = S[k * SS + j], lj = LC[k * SS + j];
+                const double rco = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + so;
+                const double ds = -rco - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
+                const double sj = so + a * ds, rc = (1.0 - a) * rco;
+                S[k * SS + j] = sj;
                 const double cc = sj * lj;
                 cs += cc; cmx = fmax(cmx, cc); cmn = fmin(cmn, cc);
                 rin = fmax(rin, fmax(fabs(rc), rc - sj));
+                const double is = rcp_t(sj), sg = lj * is, tt = lj * (rc - sj) * is;
+                d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
+                o01 += r[0] * r[1] * sg; o02 += r[0] * r[2] * sg; o12 += r[1] * r[2] * sg;
+                t0 += r[0] * is; t1 += r[1] * is; t2 += r[2] * is;
+                g0 += r[0] * tt; g1 += r[1] * tt; g2 += r[2] * tt;
             }
+            tmp[0] = (float)d0; tmp[1] = (float)d1; tmp[2] = (float)d2;
+            tmp[3] = (float)t0; tmp[4] = (float)t1; tmp[5] = (float)t2;
+            tmp[6] = (float)g0; tmp[7] = (float)g1; tmp[8] = (float)g2;
+            phi[17] = (float)o01; phi[18] = (float)o02; phi[19] = (float)o12;
+            phi[20] = (float)(-2.0 * HDR[k * ML::HDR_S + 8]);
         }
-        for (int e = lane; e < N * NZ; e += 32) {
-            if (!(e < 8 || e >= NZ)) continue;
-            const int i = e % NZ;
-            const double zi = Z[e];
-            const double cl = (zi - BND[i]) * ZL[e], cu = (BND[NZ + i] - zi) * ZU[e];
-            cs += cl + cu;
-            cmx = fmax(cmx, fmax(cl, cu));
-            cmn = fmin(cmn, fmin(cl, cu));
-        }
-        rin_n = warp_max(rin); rcomp = warp_max(cmx);
-        csum = warp_sum(cs); cmin = warp_min(cmn);
-    }
-
-    // ------------------------- barrier-augmented stage Hessian and right-hand side (-> fp32) ---
-    // rhs = r + (z_l - mu/s_l) - (z_u - mu/s_u) + A'((mu + lambda r_c)/s - lambda): the stationarity residual r is
-    // in G (single precision), the complementarity terms are formed in double precision from the iterate.
-    __device__ void assemble(double mu_t)
-    {
+        __syncwarp();
         for (int e = lane; e < N * NZ; e += 32) {
             const int k = e / NZ, i = e - k * NZ;
             float* phi = PHID + k * ML::PHI_S;
             if (e < 8 || e >= NZ) {
-                const double zi = Z[e], zl = ZL[e], zu = ZU[e];
-                const double isl = rcp_t(zi - BND[i]), isu = rcp_t(BND[NZ + i] - zi);
-                phi[i] = (float)(cost_hess_diag<double>(i, HDR + k * ML::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu);
-                G[e] = (float)((double)G[e] + ((zl - mu_t * isl) - (zu - mu_t * isu)));
-            } else {
+                const double zi = Z[e] + a * (double)DZ[e], zl = ZL[e], zu = ZU[e];
+                Z[e] = zi;
+                const double sl = zi - BND[i], su = BND[NZ + i] - zi;
+                const double cl = sl * zl, cu = su * zu;
+                cs += cl + cu;
+                cmx = fmax(cmx, fmax(cl, cu));
+                cmn = fmin(cmn, fmin(cl, cu));
+                const double isl = rcp_t(sl), isu = rcp_t(su);
+                double ph = cost_hess_diag<double>(i, HDR + k * ML::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu;
+                double gp = (double)G[e] + (zl - zu), tc = isu - isl;
+                if (i >= 8 && i < 11) {                        // k > 0 here: the rows' sums of this stage's position entries
+                    const float* tmp = DY + k * NXI;
+                    ph += (double)tmp[i - 8]; tc += (double)tmp[i - 5]; gp += (double)tmp[i - 2];
+                }
+                phi[i] = (float)ph;
+                G[e] = (float)gp;
+                DZ[e] = (float)tc;
+            } else {                                           // stage-0 states: fixed by the xinit equality
                 phi[i] = 1.0f;
                 G[e] = 0.0f;
+                DZ[e] = 0.0f;
             }
         }
-        __syncwarp();
-        for (int k = lane; k < N; k += 32) {
-            float* phi = PHID + k * ML::PHI_S;
-            double o01 = 0.0, o02 = 0.0, o12 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            const int m = live(k);
-            for (int j = 0; j < m; j++) {
-                double r[4]; load_row(k, j, r);
-                const double sj = S[k * SS + j], lj = LC[k * SS + j], is = rcp_t(sj);
-                const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                const double sg = lj * is, tt = (mu_t + lj * (rc - sj)) * is;
-                d0 += r[0] * r[0] * sg; d1 += r[1] * r[1] * sg; d2 += r[2] * r[2] * sg;
-                o01 += r[0] * r[1] * sg; o02 += r[0] * r[2] * sg; o12 += r[1] * r[2] * sg;
-                g0 += r[0] * tt; g1 += r[1] * tt; g2 += r[2] * tt;
-            }
-            phi[8] = (float)((double)phi[8] + d0); phi[9] = (float)((double)phi[9] + d1); phi[10] = (float)((double)phi[10] + d2);
-            phi[17] = (float)o01; phi[18] = (float)o02; phi[19] = (float)o12;
-            phi[20] = (float)(-2.0 * HDR[k * ML::HDR_S + 8]);
-            if (k > 0) {
-                G[k * NZ + 8] = (float)((double)G[k * NZ + 8] + g0);
-                G[k * NZ + 9] = (float)((double)G[k * NZ + 9] + g1);
-                G[k * NZ + 10] = (float)((double)G[k * NZ + 10] + g2);
-            }
-        }
+        rin_n = warp_max(rin); rcomp = warp_max(cmx);
+        csum = warp_sum(cs); cmin = warp_min(cmn);
+    }
+    // rhs = G + mu_t * T, in single precision (both are single-precision arrays by now)
+    __device__ void finish_rhs(double mu_t)
+    {
+        const float m = (float)mu_t;
+        for (int e = lane; e < N * NZ; e += 32) G[e] = fmaf(m, DZ[e], G[e]);
     }
 
     // ------------------------------------------- multiplier steps, fraction to boundary ---
@@ -355,23 +366,6 @@ template <int N> struct MixedSolver {
         }
     }
 
-    // ------------------------------------------------------- accept the primal step ----
-    __device__ void update_primal(double a)
-    {
-        for (int k = lane; k < N; k += 32) {               // corridor slacks first: they read the old position
-            const int m = live(k);
-            for (int j = 0; j < m; j++) {
-                double r[4]; load_row(k, j, r);
-                const double sj = S[k * SS + j];
-                const double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                const double ds = -rc - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
-                S[k * SS + j] = sj + a * ds;
-            }
-        }
-        __syncwarp();
-        for (int e = lane; e < N * NZ; e += 32) Z[e] += a * (double)DZ[e];
-        for (int e = NXI + lane; e < N * NXI; e += 32) Y[e] += a * (double)DY[e];
-    }
 };
 
 // =====================================================================================
@@ -480,9 +474,11 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
         infeasible0 = v0 > o.tol_ineq;
         if (infeasible0) { flag = -7; rin_n = v0; }
     }
+    double a_acc = 0.0;                       // primal step accepted by the last line search (0: the initial point)
     for (it = 0; !infeasible0; it++) {
         double csum, cmin;
-        s.residuals(rin_n, rcomp, csum, cmin);
+        s.post_step(a_acc, rin_n, rcomp, csum, cmin);     // take the step, measure the new point, start the next system
+        __syncwarp();
         mu = csum / (double)ncomp;
         const bool finite = isfinite(rs_n) && isfinite(req_n) && isfinite(mu) && isfinite(f_cur) && isfinite(th_cur);
         if (!finite) { flag = (it == 0) ? -6 : -7; break; }
@@ -495,7 +491,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
             sigma = 0.1 * q * q * q;
         }
         const double mu_t = fmax(sigma * mu, o.mu_floor);
-        s.assemble(mu_t);
+        s.finish_rhs(mu_t);
         __syncwarp();
         bool ok;
         {
@@ -532,7 +528,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
         }
         nbt_total += nbt;
         alpha_p = a; alpha_d = ad;
-        s.update_primal(a);
+        a_acc = a;                      // taken by post_step() at the top of the next pass
         f_cur = ft; th_cur = tht; ls_cur = lst; req_n = reqt; rs_n = rst;
         __syncwarp();
     }

@@ -12,6 +12,9 @@ quantities, so the two check each other.
 One deliberate deviation: the reference accumulates `temp += sqrt(X.trace())` into an UNINITIALISED
 `double temp;` (nmpc_solver.cpp:573, :597 -- undefined behaviour; whatever the stack held).  Here, and in
 the kernel, temp starts at 0, which is what the formula means (SURVEY.md §8f rank 2 notes the bug).
+A second one: `updateMatrix` never assigns At_(5,8) (no thrust term in d acc_z / d yaw), it only accumulates into it
+(`At_(5,8) += ...`, :689) on the class member At_ -- in the reference that entry keeps growing over the 20 stages of a
+replan and across replans.  `update_matrix` below (and the kernel) builds every stage's At from zero.
 """
 from __future__ import annotations
 

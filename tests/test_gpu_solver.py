@@ -372,23 +372,32 @@ def test_mixed_precision_kkt_points_pass_forcespro_acceptance_with_reference_cal
 
 def test_mixed_precision_hands_unsolved_problems_to_the_fp64_kernel():
     """The safety net, made deterministic: with an iteration cap of 3 the mixed kernel leaves every problem at exit
-    flag 0, so ALL of them are re-solved by the fp64 kernel (from the float / double arrays of the caller, on the
-    same stream) -- the results must be exactly the fp64 kernel's own with that cap, and carry the re-solve mark.
+    flag 0, so ALL of them are re-solved by the fp64 kernel (reading / writing the caller's float or double arrays, on the
+    same stream).  A problem given up at -5 / 0 restarts from the mixed kernel's last iterate with a small barrier
+    (mu0 = 0.1): the results must be exactly what the fp64 kernel produces from that start, and carry the re-solve mark.
     opts.mixed = -1 switches the net off."""
     b = W.config3(300)
     o = _lib.default_opts(maxit=3)
-    ref = S.solve_host(b, np.float64, opts=o)
-    assert np.all(ref.flag == 0) and np.all(ref.it == 3)
+    off = S.solve_host(b, np.float64, opts=_lib.default_opts(maxit=3, mixed=-1), mixed=True)      # the mixed kernel alone
+    assert np.all(off.resolved == 0) and np.all(off.flag == 0) and np.all(off.it == 3)
+    ref0 = S.solve_host(b, np.float64, opts=o)
+    assert np.max(np.abs(off.z - ref0.z)) < 1e-3         # three iterations of the same algorithm in mixed precision
     m = S.solve_host(b, np.float64, opts=o, mixed=True)
-    assert np.all(m.resolved == 1) and np.array_equal(m.z, ref.z) and np.array_equal(m.flag, ref.flag)
+    restart = W.Batch(b.xinit, off.z.copy(), b.hdr, b.rows, b.nrows, b.variant)
+    ref = S.solve_host(restart, np.float64, opts=_lib.default_opts(maxit=3, mu0=0.1))
+    assert np.all(m.resolved == 1) and np.array_equal(m.z, ref.z) and np.array_equal(m.flag, ref.flag) and np.array_equal(m.it, ref.it)
     # float arrays: the fp64 kernel reads and writes them directly (io32)
+    off32 = S.solve_host(b, np.float32, opts=_lib.default_opts(maxit=3, mixed=-1))
     b32 = b.astype(np.float32).astype(np.float64)
-    ref32 = S.solve_host(b32, np.float64, opts=o)
+    restart32 = W.Batch(b32.xinit, off32.z.astype(np.float64), b32.hdr, b32.rows, b32.nrows, b32.variant)
+    ref32 = S.solve_host(restart32, np.float64, opts=_lib.default_opts(maxit=3, mu0=0.1))
     m32 = S.solve_host(b, np.float32, opts=o)
     assert np.all(m32.resolved == 1) and np.array_equal(m32.z, ref32.z.astype(np.float32))
-    off = S.solve_host(b, np.float64, opts=_lib.default_opts(maxit=3, mixed=-1), mixed=True)
-    assert np.all(off.resolved == 0) and np.all(off.flag == 0)
-    assert np.max(np.abs(off.z - ref.z)) < 1e-3         # three iterations of the same algorithm in mixed precision
+    # NaN input: nothing to restart from -- the re-solve starts from the caller's guess and reports the bad input itself
+    bad = W.config3(8)
+    bad.hdr[2, 5, 1] = np.nan
+    r = S.solve_host(bad, np.float64, mixed=True)
+    assert r.flag[2] in (-6, -7) and np.all(np.delete(r.flag, 2) == 1)
 
 
 def test_receding_horizon_stream_matches_cpu_closed_loop():
