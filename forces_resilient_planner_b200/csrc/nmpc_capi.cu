@@ -936,10 +936,11 @@ int nmpc_adopt_plans_f64(int B, int N, const double* z_new, const int* info_int,
 
 int nmpc_rank_longest_first(int B, const int* info_int, int* order, void* stream)
 {
-    if (B < 0 || B > 12288) return fail(NMPC_ERR_ARG, "bad argument: B=%d (one CTA ranks at most 12288 agents)", B);
+    if (B < 0 || B > 12288) return fail(NMPC_ERR_ARG, "bad argument: B=%d (the keys of at most 12288 agents fit the default 48 KB of shared memory)", B);
     if (B == 0) return 0;
     if (!info_int || !order) return fail(NMPC_ERR_ARG, "null pointer argument");
-    nmpc::rank_longest_first_kernel<<<1, 1024, (size_t)B * sizeof(int), reinterpret_cast<cudaStream_t>(stream)>>>(B, info_int, order);
+    nmpc::rank_longest_first_kernel<<<(B + nmpc::RANK_THREADS - 1) / nmpc::RANK_THREADS, nmpc::RANK_THREADS, (size_t)B * sizeof(int),
+                                      reinterpret_cast<cudaStream_t>(stream)>>>(B, info_int, order);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -220,9 +220,15 @@ __device__ __forceinline__ double rsqrt_t(double x)
 __device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
 // 1/x for the slacks of the barrier terms (1e-10 .. 1e2): single-precision SFU seed + two Newton steps, 9 instructions
 // instead of the ~28 of an IEEE double division; error at rounding level (the seed's 2^-23 squared twice)
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // one MUFU.RCP, relative error 2^-23
+    return r;
+}
 __device__ __forceinline__ double rcp_t(double x)
 {
-    double r = (double)__frcp_rn((float)x);
+    double r = (double)rcp_approx((float)x);
     r = r * (2.0 - x * r);
     r = r * (2.0 - x * r);
     return r;

@@ -151,23 +151,25 @@ __global__ void adopt_plans_kernel(int B, int N, const double* z_new, const int*
 
 // order[r] = index of the agent with the r-th largest key, key = iterations of the last solve (+1000 for a failed one),
 // ties by agent index: the launch order of the next warm solve (longest first, see nmpc_solve_batch_ordered_f64).
-// One CTA, one thread per agent (B <= 1024 per CTA tile; larger fleets loop): a rank count, O(B^2 / threads) compares
-// out of shared memory -- 1024 agents: 1 M compares, a few microseconds; no library sort on the replan path.
+// Rank by counting: every CTA stages all B keys in shared memory and ranks its own 128 agents against them
+// (B compares per thread, B / 128 CTAs side by side: 1024 agents in ~5 us); no library sort on the replan path.
+constexpr int RANK_THREADS = 128;
 __global__ void rank_longest_first_kernel(int B, const int* info_int, int* order)
 {
     extern __shared__ int keys[];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
         keys[b] = info_int[(size_t)b * 4 + 1] + (info_int[(size_t)b * 4] != 1 ? 1000 : 0);
     __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const int kb = keys[b];
-        int rank = 0;
-        for (int c = 0; c < B; c++) {
-            const int kc = keys[c];
-            rank += (kc > kb) || (kc == kb && c < b);
-        }
-        order[rank] = b;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int kb = keys[b];
+    int rank = 0;
+#pragma unroll 4
+    for (int c = 0; c < B; c++) {
+        const int kc = keys[c];
+        rank += (kc > kb) || (kc == kb && c < b);
     }
+    order[rank] = b;
 }
 
 struct SampleParams {

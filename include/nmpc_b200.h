@@ -248,7 +248,7 @@ int nmpc_adopt_plans_f64(int B, int N, const double *z_new, const int *info_int,
                          const double *odom, double *z_prev, int *cold, int wrap_yaw, void *cuda_stream);
 /* order [B] <- agent indices sorted by the previous solve's iteration count, longest first (failed agents, which
  * restart cold, first; ties by index): the launch order for nmpc_solve_batch_ordered_f64 in a receding-horizon
- * stream.  One CTA, rank by counting out of shared memory; B <= 12288.                                      */
+ * stream.  Rank by counting out of shared memory (every CTA ranks 128 agents against all keys); B <= 12288.                                      */
 int nmpc_rank_longest_first(int B, const int *info_int, int *order, void *cuda_stream);
 
 /* ---- reference sampling + yaw reference, device-resident ---------------

@@ -6,6 +6,7 @@ timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 800 gpurun_out/r02_bench.err
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r02_bench_reference_arm.json 2>> gpurun_out/r02_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_value_e2e.csv python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/ncu_launch2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc_ipm_kernel -s 4 -c 1 -f -o gpurun_out/r02_fused_fp64 python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/ncu_fused.log 2>&1
 bash scripts/ncu_digest.sh gpurun_out/r02_fused_fp64.ncu-rep gpurun_out/r02_fused_fp64 "backward:nmpc_ipm.cuh@500-670" "rollout:nmpc_ipm.cuh@671-760" "costates:nmpc_ipm.cuh@890-930" "evaluate:nmpc_ipm.cuh@330-385" "residuals:nmpc_ipm.cuh@386-430" "assemble:nmpc_ipm.cuh@431-470" "step_lengths:nmpc_ipm.cuh@935-985" "update:nmpc_ipm.cuh@986-1030" "helpers:nmpc_ipm.cuh@140-329" "model:nmpc_model.cuh@1-300"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc_ipm_mixed -s 1 -c 1 -f -o gpurun_out/r02_fused_mixed python scripts/mixed_probe.py --config 2 --reps 1 > gpurun_out/ncu_mixed.log 2>&1
