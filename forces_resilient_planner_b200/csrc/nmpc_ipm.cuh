@@ -486,6 +486,117 @@ template <typename T, int N, bool PC = false> struct Solver {
         }
     }
 
+    // ------------- accept the step, measure the new point, assemble the next Newton system (default algorithm) ----
+    // What update() + residuals() + assemble() do one after the other, in one sweep over the corridor rows, one over
+    // the (stage, variable) pairs and one over the stages (used when PC is off; the predictor-corrector keeps the
+    // three separate phases, its affine analysis sits between them):
+    //   * the accepted step: s += a ds, lambda += ad dlambda, z_l / z_u += ad d(.), z += a dz, y += a (y_new - y);
+    //     mu_p is the barrier target the multiplier steps were computed for;
+    //   * the four residual norms of the NEW point (the rows are linear: their residual shrinks by 1 - a) and the
+    //     complementarity sum / max / min;
+    //   * the barrier-augmented stage Hessians, and the gradient of the next QP in a form that does not need the next
+    //     barrier target yet (it follows from the complementarity sum this pass produces):
+    //         g~ = [grad f + A' lambda r_c / s]  +  mu_t [1/s_u - 1/s_l + A'(1/s)]  =  G + mu_t * T,
+    //     T parked in the dead step array dz, the rows' partial sums in the dead costate array p; finish_rhs(mu_t)
+    //     adds mu_t * T.   a = ad = 0 with dz = 0 is the initial point.
+    __device__ void post_step(T mu_p, T a, T ad, T& rs_n, T& req_n, T& rin_n, T& rcomp, T& csum, T& cmin)
+    {
+        T rs = T(0), req = T(0), rin = T(0), cmx = T(0), cs = T(0), cmn = T(1e30);
+        for (int e = NXI + lane; e < N * NXI; e += 32) Y[e] += a * (P[e] - Y[e]);
+        __syncwarp();                                          // the costates are dead from here: rows park their sums there
+        for (int k = lane; k < N; k += 32) {
+            T* phi = PHID + k * L::PHI_S;
+            T* tmp = P + k * NXI;                              // d0 d1 d2 | t0 t1 t2 | g0 g1 g2 | al0 al1 al2
+            T acc[12];
+#pragma unroll
+            for (int q = 0; q < 12; q++) acc[q] = T(0);
+            T o01 = T(0), o02 = T(0), o12 = T(0);
+            const int m = live(k);
+            for (int j = 0; j < m; j++) {
+                T r[4]; load_row(k, j, r);
+                const T so = S[k * SS + j], lo = LC[k * SS + j];
+                const T rco = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + so;
+                const T ds = -rco - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
+                const T sj = so + a * ds, lj = lo + ad * ((mu_p - lo * ds) * rcp_t(so) - lo), rc = (T(1) - a) * rco;
+                S[k * SS + j] = sj;
+                LC[k * SS + j] = lj;
+                const T cc = sj * lj;
+                cs += cc; cmx = fmax(cmx, cc); cmn = fmin(cmn, cc);
+                rin = fmax(rin, fmax(fabs(rc), rc - sj));
+                const T is = rcp_t(sj), sg = lj * is, tt = lj * rc * is;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    acc[c] += r[c] * r[c] * sg; acc[3 + c] += r[c] * is; acc[6 + c] += r[c] * tt; acc[9 + c] += r[c] * lj;
+                }
+                o01 += r[0] * r[1] * sg; o02 += r[0] * r[2] * sg; o12 += r[1] * r[2] * sg;
+            }
+#pragma unroll
+            for (int q = 0; q < 12; q++) tmp[q] = acc[q];
+            phi[17] = o01; phi[18] = o02; phi[19] = o12;
+            phi[20] = T(-2) * HDR[k * L::HDR_S + 8];   // H[u_i][uprev_i]
+        }
+        __syncwarp();
+        for (int e = lane; e < N * NZ; e += 32) {
+            const int k = e / NZ, i = e - k * NZ;
+            T* phi = PHID + k * L::PHI_S;
+            if (e < 8 || e >= NZ) {
+                const T zo = Z[e], dzi = DZ[e], zlo = ZL[e], zuo = ZU[e];
+                const T islo = rcp_t(zo - BND[i]), isuo = rcp_t(BND[NZ + i] - zo);
+                const T zl = zlo + ad * ((mu_p - zlo * dzi) * islo - zlo), zu = zuo + ad * ((mu_p + zuo * dzi) * isuo - zuo);
+                const T zi = zo + a * dzi;
+                Z[e] = zi; ZL[e] = zl; ZU[e] = zu;
+                const T sl = zi - BND[i], su = BND[NZ + i] - zi;
+                const T cl = sl * zl, cu = su * zu;
+                cs += cl + cu;
+                cmx = fmax(cmx, fmax(cl, cu));
+                cmn = fmin(cmn, fmin(cl, cu));
+                const T isl = rcp_t(sl), isu = rcp_t(su);
+                T ph = cost_hess_diag<T>(i, HDR + k * L::HDR_S, k == 0, final_variant && k == N - 1) + zl * isl + zu * isu;
+                T tc = isu - isl;
+                if (i >= 8 && i < 11) { ph += P[k * NXI + i - 8]; tc += P[k * NXI + i - 5]; }
+                phi[i] = ph;
+                DZ[e] = tc;
+            } else {                                           // stage-0 states: fixed by the xinit equality
+                phi[i] = T(1);
+                DZ[e] = T(0);
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < N; k += 32) {
+            const T* tmp = P + k * NXI;
+            const T* yn = Y + (k + 1) * NXI;   // only dereferenced for k < N-1
+            const T* yk = Y + k * NXI;         // row 0 stays zero
+            const T* jc = JC + k * NJC;
+            const int nfree = (k == 0) ? 8 : NZ;
+#pragma unroll 1
+            for (int i = 0; i < nfree; i++) {
+                T r = G[k * NZ + i] - ZL[k * NZ + i] + ZU[k * NZ + i];
+                if (k < N - 1) r += jt_y<T>(jc, yn, i);
+                if (i >= 8) r -= yk[i - 8];
+                else if (i >= 4) r -= yk[5 + i];
+                if (i >= 8 && i < 11) r += tmp[1 + i];          // A' lambda
+                rs = fmax(rs, fabs(r));
+            }
+            if (k < N - 1) {
+#pragma unroll
+                for (int i = 0; i < NXI; i++) req = fmax(req, fabs(D[k * NXI + i]));
+            }
+            if (k > 0) {
+                G[k * NZ + 8] += tmp[6]; G[k * NZ + 9] += tmp[7]; G[k * NZ + 10] += tmp[8];
+            } else {
+#pragma unroll
+                for (int i = 8; i < NZ; i++) G[i] = T(0);
+            }
+        }
+        rs_n = warp_max(rs); req_n = warp_max(req); rin_n = warp_max(rin); rcomp = warp_max(cmx);
+        csum = warp_sum(cs); cmin = warp_min(cmn);
+    }
+    // gradient of the QP: G + mu_t * T
+    __device__ void finish_rhs(T mu_t)
+    {
+        for (int e = lane; e < N * NZ; e += 32) G[e] += mu_t * DZ[e];
+    }
+
     // ------------------------------------------------------------- Riccati backward -----
     // Four warp-synchronous phases per stage:
     //   A: PF = P+(:,x) F,  tv = p+ + P+ d           B: Q blocks (F' PF + coupling), q~ vectors
@@ -1162,9 +1273,15 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         infeasible0 = v0 > (T)o.tol_ineq;
         if (infeasible0) { flag = -7; rin_n = v0; }
     }
+    T a_acc = T(0), ad_acc = T(0), mu_acc = mu0;     // the step accepted by the last line search (none yet)
+    if constexpr (!PC) {
+        for (int e = lane; e < N * NXI; e += 32) s.P[e] = T(0);
+        __syncwarp();
+    }
     for (it = 0; !infeasible0; it++) {
         T csum, cmin;
-        s.residuals(rs_n, req_n, rin_n, rcomp, csum, cmin);
+        if constexpr (PC) s.residuals(rs_n, req_n, rin_n, rcomp, csum, cmin);
+        else s.post_step(mu_acc, a_acc, ad_acc, rs_n, req_n, rin_n, rcomp, csum, cmin);
         mu = csum / (T)ncomp;
         const bool finite = isfinite(rs_n) && isfinite(req_n) && isfinite(mu) && isfinite(f_cur) && isfinite(th_cur);
         if (!finite) { flag = (it == 0) ? -6 : -7; break; }
@@ -1204,7 +1321,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
             s.unpark(parked);
             __syncwarp();
         } else {
-            s.assemble(mu_t);
+            s.finish_rhs(mu_t);
             __syncwarp();
             T parked[L::NPARK_LANE];
             s.park(parked);                 // z, z_l, z_u, y, ... leave shared memory for the sweeps
@@ -1239,7 +1356,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
         }
         nbt_total += nbt;
         alpha_p = a; alpha_d = ad;
-        s.update(mu_t, a, ad, dza);     // gradient / Jacobians / defects of the accepted trial stay in place
+        if constexpr (PC) s.update(mu_t, a, ad, dza);     // gradient / Jacobians / defects of the accepted trial stay in place
+        else { a_acc = a; ad_acc = ad; mu_acc = mu_t; }   // taken by post_step() at the top of the next pass
         f_cur = ft; th_cur = tht; ls_cur = lst;
         __syncwarp();
     }
