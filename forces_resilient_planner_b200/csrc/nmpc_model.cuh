@@ -99,17 +99,37 @@ __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(
 __device__ __forceinline__ double log_t(double x) { return log(x); }
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
 
+// sin / cos of the three Euler angles, packed (sr cr sp cp sy cy)
+template <typename T> __device__ __forceinline__ void trig3(const T r[3], T sc[6])
+{
+    sincos_t(r[0], &sc[0], &sc[1]);
+    sincos_t(r[1], &sc[2], &sc[3]);
+    sincos_t(r[2], &sc[4], &sc[5]);
+}
+// The same for r + dr with |dr| small, from the values at r by the addition theorems: the Heun step evaluates the
+// attitude a second time at rpy + h * rates, and |h * rate| <= 0.05 * pi/2 = 0.079 for every point inside the rate bounds
+// (mpc_generator_normal.m:33-35).  Taylor polynomials of sin / cos through x^9 / x^10: truncation < 1e-19 there and
+// still < 5e-14 at |dr| = 0.3 (four times the bound) -- 3 x ~20 flops instead of three more sincos calls.
+template <typename T> __device__ __forceinline__ void trig3_shifted(const T sc[6], const T dr[3], T out[6])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const T x = dr[i], x2 = x * x;
+        const T sd = x * (T(1) + x2 * (T(-1.0 / 6) + x2 * (T(1.0 / 120) + x2 * (T(-1.0 / 5040) + x2 * T(1.0 / 362880)))));
+        const T cd = T(1) + x2 * (T(-0.5) + x2 * (T(1.0 / 24) + x2 * (T(-1.0 / 720) + x2 * (T(1.0 / 40320) + x2 * T(-1.0 / 3628800)))));
+        out[2 * i] = sc[2 * i] * cd + sc[2 * i + 1] * sd;
+        out[2 * i + 1] = sc[2 * i + 1] * cd - sc[2 * i] * sd;
+    }
+}
+
 // acc = z_B T/m + f_ext - g e3 - kd (v - z_B (z_B.v));  R diag(kd,kd,0) R' = kd (I - z_B z_B')
-// JAC: also Av = da/dv, Ar = da/drpy (row-major 3x3), AT = da/dT.
+// sc = (sin, cos) of roll, pitch, yaw.  JAC: also Av = da/dv, Ar = da/drpy (row-major 3x3), AT = da/dT.
 template <typename T, bool JAC>
-__device__ __forceinline__ void accel(const T v[3], const T r[3], T thrust, const T fe[3], T a[3],
+__device__ __forceinline__ void accel(const T v[3], const T sc[6], T thrust, const T fe[3], T a[3],
                                       T Av[9], T Ar[9], T AT[3])
 {
     using C = Const<T>;
-    T sr, cr, sp, cp, sy, cy;
-    sincos_t(r[0], &sr, &cr);
-    sincos_t(r[1], &sp, &cp);
-    sincos_t(r[2], &sy, &cy);
+    const T sr = sc[0], cr = sc[1], sp = sc[2], cp = sc[3], sy = sc[4], cy = sc[5];
     T zb[3] = {cy * sp * cr + sy * sr, sy * sp * cr - cy * sr, cp * cr};
     T zv = zb[0] * v[0] + zb[1] * v[1] + zb[2] * v[2];
     T tm = thrust * (T(1) / C::mass);
@@ -147,14 +167,17 @@ __device__ __forceinline__ void dynamics(const T z[NZ], const T fe[3], T c[NXI],
     const T* v = z + 11;
     const T* r = z + 14;
     T a1[3], A1v[9], A1r[9], A1T[3], a2[3], A2v[9], A2r[9], A2T[3];
-    accel<T, JAC>(v, r, z[3], fe, a1, A1v, A1r, A1T);
-    T v2[3], r2[3];
+    T sc1[6], sc2[6];
+    trig3<T>(r, sc1);
+    accel<T, JAC>(v, sc1, z[3], fe, a1, A1v, A1r, A1T);
+    T v2[3], dr[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         v2[i] = v[i] + h * a1[i];
-        r2[i] = r[i] + h * w[i];
+        dr[i] = h * w[i];
     }
-    accel<T, JAC>(v2, r2, z[3], fe, a2, A2v, A2r, A2T);
+    trig3_shifted<T>(sc1, dr, sc2);
+    accel<T, JAC>(v2, sc2, z[3], fe, a2, A2v, A2r, A2T);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         c[i] = p[i] + h * v[i] + hh * a1[i];
@@ -168,16 +191,16 @@ __device__ __forceinline__ void dynamics(const T z[NZ], const T fe[3], T c[NXI],
         for (int i = 0; i < 3; i++) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                T dv = T(0), dr = A2r[3 * i + j];
+                T dv = T(0), dr2 = A2r[3 * i + j];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     dv += A2v[3 * i + k] * ((k == j ? T(1) : T(0)) + h * A1v[3 * k + j]);
-                    dr += A2v[3 * i + k] * h * A1r[3 * k + j];
+                    dr2 += A2v[3 * i + k] * h * A1r[3 * k + j];
                 }
                 jc[JPV + 3 * i + j] = (i == j ? h : T(0)) + hh * A1v[3 * i + j];
                 jc[JPR + 3 * i + j] = hh * A1r[3 * i + j];
                 jc[JVV + 3 * i + j] = (i == j ? T(1) : T(0)) + h2 * (A1v[3 * i + j] + dv);
-                jc[JVR + 3 * i + j] = h2 * (A1r[3 * i + j] + dr);
+                jc[JVR + 3 * i + j] = h2 * (A1r[3 * i + j] + dr2);
                 jc[JVW + 3 * i + j] = hh * A2r[3 * i + j];
             }
             T dT = A2T[i];
