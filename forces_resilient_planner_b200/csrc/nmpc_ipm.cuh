@@ -161,7 +161,7 @@ template <typename T> __device__ __forceinline__ T warp_min(T v)
     return v;
 }
 template <typename T> struct Eps;
-template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int logvars = 8, logrows = 8; };
+template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; static constexpr int logvars = 9, logrows = 8; };
 template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f; static constexpr int logvars = 1, logrows = 2; };
 
 __device__ __forceinline__ int e_col(int i) { return i < 9 ? 8 + i : i - 5; }   // xi index -> z index

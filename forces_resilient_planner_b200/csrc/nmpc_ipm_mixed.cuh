@@ -195,7 +195,7 @@ template <int N> struct MixedSolver {
                 double sl = zk[i] - lower_bound<double>(i), su = upper_bound<double>(i) - zk[i];
                 if (i >= 8 && k == 0) { sl = 1.0; su = 1.0; }
                 prod *= sl * su;
-                if (i % 8 == 7 || i == NZ - 1) { ls += log(prod); prod = 1.0; }     // <= 16 slacks per product: no underflow
+                if (i % 9 == 8 || i == NZ - 1) { ls += log(prod); prod = 1.0; }     // <= 18 slacks per product: no underflow
             }
             const int m = live(k);
             double al0 = 0.0, al1 = 0.0, al2 = 0.0;
