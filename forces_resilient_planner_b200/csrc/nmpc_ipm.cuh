@@ -1281,7 +1281,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     for (it = 0; !infeasible0; it++) {
         T csum, cmin;
         if constexpr (PC) s.residuals(rs_n, req_n, rin_n, rcomp, csum, cmin);
-        else s.post_step(mu_acc, a_acc, ad_acc, rs_n, req_n, rin_n, rcomp, csum, cmin);
+        else { s.post_step(mu_acc, a_acc, ad_acc, rs_n, req_n, rin_n, rcomp, csum, cmin); __syncwarp(); }   // G is complete for finish_rhs()
         mu = csum / (T)ncomp;
         const bool finite = isfinite(rs_n) && isfinite(req_n) && isfinite(mu) && isfinite(f_cur) && isfinite(th_cur);
         if (!finite) { flag = (it == 0) ? -6 : -7; break; }
