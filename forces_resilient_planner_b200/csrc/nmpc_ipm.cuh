@@ -203,37 +203,33 @@ __device__ __forceinline__ void tma_store(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// in-register Cholesky of a 4x4 SPD matrix given row-major a[16] (lower triangle used); L (10 values)
-// as l[10] = {l00, l10,l11, l20,l21,l22, l30,l31,l32,l33}, li[4] = 1/diag (no divisions anywhere:
-// 1/sqrt(d) comes from rsqrt); returns false on a non-positive pivot.
-// 1/sqrt(x) in double precision from the single-precision SFU seed and two Newton steps (relative error 2^-22 -> 2^-43 ->
-// rounding level): 12 instructions on the critical path of every pivot instead of the ~30 of the library routine.
-// The pivots of the 4x4 blocks (1e-3 .. 1e12) are far inside the single-precision exponent range.
+// 1/sqrt(x) and 1/x in double precision from the SFU's double-precision seeds (rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64:
+// MUFU.RSQ64H / MUFU.RCP64H on the upper word, relative error 2^-22) and two Newton steps (2^-22 -> 2^-44 -> rounding
+// level): about ten instructions on the critical path of every pivot / barrier slack instead of the ~30 of the library
+// routine or of an IEEE division, and no double <-> float conversions.  Arguments are pivots of the 4x4 blocks and
+// barrier slacks: normal, positive numbers (a non-positive pivot is caught before its root is used).
 __device__ __forceinline__ double rsqrt_t(double x)
 {
-    double y = (double)rsqrtf((float)x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double hx = 0.5 * x;
     y = y * (1.5 - hx * y * y);
     y = y * (1.5 - hx * y * y);
     return y;
 }
 __device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
-// 1/x for the slacks of the barrier terms (1e-10 .. 1e2): single-precision SFU seed + two Newton steps, 9 instructions
-// instead of the ~28 of an IEEE double division; error at rounding level (the seed's 2^-23 squared twice)
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // one MUFU.RCP, relative error 2^-23
-    return r;
-}
 __device__ __forceinline__ double rcp_t(double x)
 {
-    double r = (double)rcp_approx((float)x);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     r = r * (2.0 - x * r);
     r = r * (2.0 - x * r);
     return r;
 }
 __device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
+// in-register Cholesky of a 4x4 SPD matrix given row-major a[16] (lower triangle used); L (10 values)
+// as l[10] = {l00, l10,l11, l20,l21,l22, l30,l31,l32,l33}, li[4] = 1/diag (no divisions anywhere:
+// 1/sqrt(d) comes from rsqrt); returns false on a non-positive pivot.
 template <typename T> __device__ __forceinline__ bool chol4(const T* a, T l[10], T li[4])
 {
     bool ok = true;

@@ -8,11 +8,11 @@ timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_value_e2e.csv python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/ncu_launch2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc_ipm_kernel -s 4 -c 1 -f -o gpurun_out/r02_fused_fp64 python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/ncu_fused.log 2>&1
-bash scripts/ncu_digest.sh gpurun_out/r02_fused_fp64.ncu-rep gpurun_out/r02_fused_fp64 "backward:nmpc_ipm.cuh@500-670" "rollout:nmpc_ipm.cuh@671-760" "costates:nmpc_ipm.cuh@890-930" "evaluate:nmpc_ipm.cuh@330-385" "residuals:nmpc_ipm.cuh@386-430" "assemble:nmpc_ipm.cuh@431-470" "step_lengths:nmpc_ipm.cuh@935-985" "update:nmpc_ipm.cuh@986-1030" "helpers:nmpc_ipm.cuh@140-329" "model:nmpc_model.cuh@1-300"
+bash scripts/ncu_digest.sh gpurun_out/r02_fused_fp64.ncu-rep gpurun_out/r02_fused_fp64 $(python scripts/phase_ranges.py nmpc_ipm.cuh nmpc_model.cuh)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc_ipm_mixed -s 1 -c 1 -f -o gpurun_out/r02_fused_mixed python scripts/mixed_probe.py --config 2 --reps 1 > gpurun_out/ncu_mixed.log 2>&1
-bash scripts/ncu_digest.sh gpurun_out/r02_fused_mixed.ncu-rep gpurun_out/r02_fused_mixed "backward:nmpc_ipm.cuh@500-670" "rollout:nmpc_ipm.cuh@671-760" "costates:nmpc_ipm.cuh@890-930" "helpers:nmpc_ipm.cuh@140-329" "evaluate:nmpc_ipm_mixed.cuh@162-228" "residuals:nmpc_ipm_mixed.cuh@229-258" "assemble:nmpc_ipm_mixed.cuh@259-299" "step_lengths:nmpc_ipm_mixed.cuh@300-335" "update_duals:nmpc_ipm_mixed.cuh@336-358" "update_primal:nmpc_ipm_mixed.cuh@359-380" "kernel:nmpc_ipm_mixed.cuh@381-600" "load_row_etc:nmpc_ipm_mixed.cuh@100-161" "model:nmpc_model.cuh@1-300"
+bash scripts/ncu_digest.sh gpurun_out/r02_fused_mixed.ncu-rep gpurun_out/r02_fused_mixed $(python scripts/phase_ranges.py nmpc_ipm.cuh nmpc_ipm_mixed.cuh nmpc_model.cuh)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc_ipm_mixed -s 1 -c 1 -f -o gpurun_out/r02_fused_mixed_c3 python scripts/mixed_probe.py --config 3 --batch 16384 --reps 1 > gpurun_out/ncu_mixed3.log 2>&1
-bash scripts/ncu_digest.sh gpurun_out/r02_fused_mixed_c3.ncu-rep gpurun_out/r02_fused_mixed_c3
+bash scripts/ncu_digest.sh gpurun_out/r02_fused_mixed_c3.ncu-rep gpurun_out/r02_fused_mixed_c3 $(python scripts/phase_ranges.py nmpc_ipm.cuh nmpc_ipm_mixed.cuh nmpc_model.cuh)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kkt_backsolve -s 6 -c 1 -f -o gpurun_out/r02_backsolve python tests/tools/bs_check.py > gpurun_out/ncu_bs.log 2>&1
 bash scripts/ncu_digest.sh gpurun_out/r02_backsolve.ncu-rep gpurun_out/r02_backsolve
 timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_small.py > gpurun_out/r02_san_mem.log 2>&1; tail -3 gpurun_out/r02_san_mem.log
