@@ -488,8 +488,7 @@ template <typename T, int N, bool PC = false> struct Solver {
     // three separate phases, its affine analysis sits between them):
     //   * the accepted step: s += a ds, lambda += ad dlambda, z_l / z_u += ad d(.), z += a dz, y += a (y_new - y);
     //     mu_p is the barrier target the multiplier steps were computed for;
-    //   * the four residual norms of the NEW point (the rows are linear: their residual shrinks by 1 - a) and the
-    //     complementarity sum / max / min;
+    //   * the four residual norms of the NEW point and the complementarity sum / max / min;
     //   * the barrier-augmented stage Hessians, and the gradient of the next QP in a form that does not need the next
     //     barrier target yet (it follows from the complementarity sum this pass produces):
     //         g~ = [grad f + A' lambda r_c / s]  +  mu_t [1/s_u - 1/s_l + A'(1/s)]  =  G + mu_t * T,
@@ -513,7 +512,11 @@ template <typename T, int N, bool PC = false> struct Solver {
                 const T so = S[k * SS + j], lo = LC[k * SS + j];
                 const T rco = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + so;
                 const T ds = -rco - (r[0] * DZ[k * NZ + 8] + r[1] * DZ[k * NZ + 9] + r[2] * DZ[k * NZ + 10]);
-                const T sj = so + a * ds, lj = lo + ad * ((mu_p - lo * ds) * rcp_t(so) - lo), rc = (T(1) - a) * rco;
+                const T sj = so + a * ds, lj = lo + ad * ((mu_p - lo * ds) * rcp_t(so) - lo);
+                // residual of the row at the new point, from the very numbers that will be in memory (not (1 - a) * rco: the
+                // rounding of z + a dz and s + a ds is part of what the next Newton step has to remove)
+                const T rc = r[0] * (Z[k * NZ + 8] + a * DZ[k * NZ + 8]) + r[1] * (Z[k * NZ + 9] + a * DZ[k * NZ + 9]) +
+                             r[2] * (Z[k * NZ + 10] + a * DZ[k * NZ + 10]) - (r[3] + C::hu) + sj;
                 S[k * SS + j] = sj;
                 LC[k * SS + j] = lj;
                 const T cc = sj * lj;

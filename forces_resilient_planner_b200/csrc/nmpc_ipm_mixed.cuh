@@ -228,8 +228,7 @@ template <int N> struct MixedSolver {
     // ------------------- accept the primal step, measure the new point, assemble the next Newton system ------
     // One pass over the corridor rows and one over the (stage, variable) pairs does what used to be three phases:
     //   * the accepted primal step: s += a ds, z += a dz, y += a dy (the multipliers were stepped before the line search);
-    //   * the residuals of the NEW point that are not evaluate()'s: inequality residual (the rows are linear: the
-    //     residual shrinks by 1 - a), complementarity products, their sum / max / min;
+    //   * the residuals of the NEW point that are not evaluate()'s: inequality residual, complementarity products, their sum / max / min;
     //   * the barrier-augmented stage Hessians, and the right-hand side in a form that does not need the barrier target
     //     yet:   rhs = [r + (z_l - z_u) + A' lambda (r_c - s)/s]  +  mu_t [1/s_u - 1/s_l + A'(1/s)]  =  G + mu_t * T.
     //     (mu_t follows from the complementarity sum this very pass produces.)  T is parked in the dead step array DZ,
@@ -252,7 +251,11 @@ template <int N> struct MixedSolver {
                 const double so = S[k * SS + j], lj = LC[k * SS + j];
                 const double rco = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + so;
                 const double ds = -rco - (r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10]);
-                const double sj = so + a * ds, rc = (1.0 - a) * rco;
+                const double sj = so + a * ds;
+                // residual of the row at the new point from the very numbers that will be in memory (not (1 - a) * rco: with
+                // slacks of 1e-9 the rounding of z + a dz and s + a ds is part of what the next Newton step has to remove)
+                const double rc = r[0] * (Z[k * NZ + 8] + a * (double)DZ[k * NZ + 8]) + r[1] * (Z[k * NZ + 9] + a * (double)DZ[k * NZ + 9]) +
+                                  r[2] * (Z[k * NZ + 10] + a * (double)DZ[k * NZ + 10]) - (r[3] + C::hu) + sj;
                 S[k * SS + j] = sj;
                 const double cc = sj * lj;
                 cs += cc; cmx = fmax(cmx, cc); cmn = fmin(cmn, cc);
