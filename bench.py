@@ -14,7 +14,9 @@ seed); the problems are independent, so the solve has no collective.
           max over ranks.
   e2e     the same through the host-pointer C ABI (nmpc_solve_batch_host_f64): pinned host
           buffers, H2D + solve + D2H inside every timed call.
-  collate (N > 1) the same step through nmpc_solve_batch_sharded_f64: every rank's kernel writes into its
+  collate (N > 1) the same step with the results collated on every rank, two ways: nmpc_solve_batch_sharded_p2p_f64 (the
+          solve kernel's epilogue stores every result into all ranks' buffers over NVLink, barrier kernels around it)
+          and, under "nccl", nmpc_solve_batch_sharded_f64: every rank's kernel writes into its
           slice of one NCCL-registered buffer and an in-place ncclAllGather on the same stream collates the
           results of all ranks on all ranks -- inside the CUDA events.  `value_with_collation`, bytes, GB/s.
   roofline           the dominant kernel (fused IPM) against its compulsory HBM traffic
@@ -349,6 +351,31 @@ def run_b200(args):
                    "api": "nmpc_solve_batch_sharded_f64: kernel writes into its slice of one ncclMemAlloc'd + registered "
                           "buffer; in-place ncclAllGather (z + info) on the same stream"}
 
+        # ---- the same step with the exchange fused into the solve kernel: peer stores over NVLink + barrier kernels ----
+        try:
+            pc = D.PeerCollator(rank, world, dev, B, HORIZON)
+        except RuntimeError as e:
+            pc = None
+            collate = {"p2p_unavailable": str(e), **collate, "method": "nccl_allgather"}
+        if pc is not None:
+            p_ms = timed(lambda: pc.solve_sharded(db, opts), args.steps, max(args.warmup, 3))
+            p_total = max_over_ranks(sum(p_ms) * 1e-3)
+            barrier_ms = max_over_ranks(float(np.mean(timed(lambda: pc.barrier(), 10, 3))))
+            pc.check()
+            p_mine_ok = bool(torch.equal(pc.z_all[rank * B:(rank + 1) * B], db.z))
+            p_same = bool(torch.equal(pc.z_all, z_all)) and bool(torch.equal(pc.info_all[:, :3], ii_all[:, :3]))
+            nccl = collate
+            collate = {"method": "peer_stores", "value_with_collation": B * world * args.steps / p_total, "unit": UNIT,
+                       "ms_per_step": 1e3 * p_total / args.steps, "peer_store_bytes_per_step_per_gpu": nbytes // world * (world - 1),
+                       "barrier_kernel_ms_alone": barrier_ms, "own_slice_identical": p_mine_ok,
+                       "identical_to_nccl_allgather_result": p_same,
+                       "converged_frac_all_ranks": float(np.mean(pc.info_all[:, 0].cpu().numpy() == 1)),
+                       "api": "nmpc_solve_batch_sharded_p2p_f64: the solve kernel's epilogue writes every problem's z and info into its "
+                              "slice of every rank's buffer (TMA bulk stores to CUDA-IPC-mapped peer memory); barrier kernel before and after",
+                       "nccl": nccl}
+            dist.barrier()
+            pc.close()
+
     extras = {}
     if not args.no_extras:
         extras.update(run_config4(args, torch, dist, D, S, W, _lib, dev, rank, world, col, max_over_ranks, sum_over_ranks))
@@ -514,9 +541,20 @@ def run_config4(args, torch, dist, D, S, W, _lib, dev, rank, world, col, max_ove
     db = S.DeviceBatch(b, np.float32, dev)
     o = _lib.default_opts()
     st = torch.cuda.current_stream(dev)
-    if col:
+    pc, method = None, "none (one GPU)"
+    if world > 1:
+        try:
+            pc = D.PeerCollator(rank, world, dev, per, N, dtype=np.float32)
+        except RuntimeError:
+            pc = None
+    if pc is not None:
+        z_all, ii_all = pc.z_all, pc.info_all
+        run = lambda: pc.solve_sharded(db, o)
+        method = "peer stores from the solve kernel's epilogue + barrier kernels (nmpc_solve_batch_sharded_p2p_f32)"
+    elif col:
         z_all = col.alloc((world * per, N, 17), torch.float32); ii_all = col.alloc((world * per, 4), torch.int32)
         run = lambda: col.solve_sharded(db, z_all, ii_all, o)
+        method = "in-place NCCL all-gather of z and info (nmpc_solve_batch_sharded_f32)"
     else:
         z_all, ii_all = db.z, db.info_int
         run = lambda: S.solve_device(db, o)
@@ -531,18 +569,23 @@ def run_config4(args, torch, dist, D, S, W, _lib, dev, rank, world, col, max_ove
     t = max_over_ranks(min(ms))
     flags = ii_all.cpu().numpy()
     mine = flags[rank * per:(rank + 1) * per]
-    cs_local = sum_over_ranks(float(db.z.double().sum().item()) if not col else float(z_all[rank * per:(rank + 1) * per].double().sum().item()))
+    cs_local = sum_over_ranks(float(db.z.double().sum().item()) if world == 1 else float(z_all[rank * per:(rank + 1) * per].double().sum().item()))
     cs_full = float(z_all.double().sum().item())
     it_sum = sum_over_ranks(float(mine[:, 1].sum())); res_sum = sum_over_ranks(float(mine[:, 3].sum()))
     it_max = max_over_ranks(float(mine[:, 1].max()))
+    conv = float(np.mean(flags[:, 0] == 1)); cs_full_ok = bool(abs(cs_full - cs_local) <= 1e-6 * abs(cs_local) + 1e-3)
+    nbytes = int(z_all.numel() * 4 + ii_all.numel() * 4) if world > 1 else 0
+    if pc is not None:
+        pc.check()
+        del z_all, ii_all
+        dist.barrier()
+        pc.close()
     return {"config4": {
         "workload": f"config4: batch=262144 (512x512 constant-wind sweep, |f| 0..4 m/s^2), N=40, float arrays, sharded {per} per GPU over "
-                    f"{world} GPU(s), mixed-precision kernel, solve + in-place NCCL all-gather of z and info",
-        "value": Btot / (t * 1e-3), "unit": UNIT, "ms_solve_plus_collation": t, "n_gpus": world,
-        "collation_bytes": int(z_all.numel() * 4 + ii_all.numel() * 4) if col else 0,
-        "converged_frac_all_ranks": float(np.mean(flags[:, 0] == 1)), "mean_iterations": it_sum / Btot, "max_iterations": int(it_max),
-        "resolved_in_fp64_frac": res_sum / Btot,
-        "checksum_of_checksums_ok": bool(abs(cs_full - cs_local) <= 1e-6 * abs(cs_local) + 1e-3)}}
+                    f"{world} GPU(s), mixed-precision kernel, solve + collation of z and info on every rank",
+        "value": Btot / (t * 1e-3), "unit": UNIT, "ms_solve_plus_collation": t, "n_gpus": world, "collation": method,
+        "collation_bytes": nbytes, "converged_frac_all_ranks": conv, "mean_iterations": it_sum / Btot, "max_iterations": int(it_max),
+        "resolved_in_fp64_frac": res_sum / Btot, "checksum_of_checksums_ok": cs_full_ok}}
 
 
 def run_config5(torch, dist, W, dev, rank, local_rank, world, max_over_ranks, sum_over_ranks, agents=1024, replans=500):

@@ -152,7 +152,7 @@ int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, cons
                  const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int,
                  void* info_real, void* stream, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
                  void* lc_out = nullptr, const int* order = nullptr, const int* count = nullptr, int io32 = 0,
-                 const void* z_warm = nullptr)
+                 const void* z_warm = nullptr, const nmpc::PeerOut* peers = nullptr)
 {
     nmpc_opts o;
     if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
@@ -163,6 +163,7 @@ int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, cons
     prm.z_warm = z_warm;
     prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
+    if (peers) prm.peers = *peers;
     std::memcpy(&prm.o, &o, sizeof(o));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return N == 20 ? launch<double, 20>(prm, st) : launch<double, 40>(prm, st);
@@ -176,7 +177,7 @@ int solve_device(int B, int N, int mcap, const void* xinit, const void* z0, cons
 int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
                 const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int, void* info_real,
                 void* stream, int io32, void* y_out = nullptr, void* zl_out = nullptr, void* zu_out = nullptr,
-                void* lc_out = nullptr, const int* order = nullptr, bool group = false)
+                void* lc_out = nullptr, const int* order = nullptr, bool group = false, const nmpc::PeerOut* peers = nullptr)
 {
     nmpc_opts o;
     if (int rc = check_solve_args(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_out, info_int, info_real, &o)) return rc;
@@ -186,6 +187,7 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
     prm.xinit = xinit; prm.z0 = z0; prm.hdr = hdr; prm.rows = rows; prm.nrows = nrows; prm.order = order;
     prm.z_out = z_out; prm.info_int = info_int; prm.info_real = info_real;
     prm.y_out = y_out; prm.zl_out = zl_out; prm.zu_out = zu_out; prm.lc_out = lc_out;
+    if (peers) prm.peers = *peers;
     std::memcpy(&prm.o, &o, sizeof(o));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // group: the low-latency variant, one warp-group (128 threads) per problem (nmpc_ipm_group.cuh)
@@ -200,7 +202,7 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
     nmpc_opts o64 = o;
     o64.pc = 0;
     int rc = solve_device(B, N, mcap, xinit, z0, hdr, rows, nrows, variant, &o64, z_out, info_int, info_real, stream,
-                          y_out, zl_out, zu_out, lc_out, ws + 4, ws, io32, /*z_warm = the mixed kernel's last iterates*/ z_out);
+                          y_out, zl_out, zu_out, lc_out, ws + 4, ws, io32, /*z_warm = the mixed kernel's last iterates*/ z_out, peers);
     CUDA_TRY(cudaFreeAsync(ws, st));
     return rc;
 }
@@ -564,6 +566,56 @@ template <typename T> int fma_probe(double* tflops)
 
 }  // namespace
 
+// ---- peer-store collation: barrier kernel and the per-rank object (entry points below) ----
+namespace {
+constexpr int PEER_HDR_BYTES = 256;            // flags[16] | epoch | status, then the collation buffers
+constexpr int PEER_EPOCH = 16, PEER_STATUS = 17;
+struct PeerSync { unsigned* hdr[nmpc::MAX_PEERS + 1]; int rank, world; };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// All ranks meet here: thread p tells rank p "rank `rank` has reached epoch e" (a release store into p's header, after
+// a system-wide fence: everything this GPU wrote to p before -- the solutions -- is visible there first) and waits for
+// p's word in its own header.  The epoch lives on the device, so a CUDA graph can replay the kernel.  A rank that does
+// not show up within two seconds sets the status word instead of hanging the GPU (nmpc_peers_status).
+__global__ void peer_barrier_kernel(PeerSync ps)
+{
+    __shared__ unsigned e_sh;
+    unsigned* mine = ps.hdr[ps.rank];
+    if (threadIdx.x == 0) e_sh = mine[PEER_EPOCH] + 1;
+    __syncthreads();
+    const unsigned e = e_sh;
+    const int p = threadIdx.x;
+    if (p < ps.world && p != ps.rank) {
+        __threadfence_system();
+        st_release_sys(ps.hdr[p] + ps.rank, e);
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(mine + p) - e) < 0)
+            if (globaltimer_ns() - t0 > 2000000000ull) { mine[PEER_STATUS] = 1; break; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) mine[PEER_EPOCH] = e;
+}
+}  // namespace
+
+struct nmpc_peers {
+    int rank = 0, world = 1, device = 0;
+    size_t z_bytes = 0, info_ints = 0, z_off = 0, info_off = 0, total = 0;
+    char* base[nmpc::MAX_PEERS + 1] = {};      // base[rank] = this rank's allocation, the others are IPC mappings
+    bool connected = false;
+};
+
 extern "C" {
 
 int nmpc_fma_peak_probe(int elem_size, double* tflops)
@@ -795,6 +847,139 @@ int nmpc_collate_inplace(nmpc_comm* comm, void* buf_all, size_t bytes_per_rank, 
 {
     if (!comm || !buf_all) return fail(NMPC_ERR_ARG, "null pointer argument");
     return collate_inplace(comm, buf_all, bytes_per_rank, nullptr, 0, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+/* ---- multi-GPU: collation by peer stores from inside the solve kernel (CUDA IPC over NVLink) ------------------- */
+int nmpc_peers_create(int world, int rank, size_t z_bytes_all, size_t info_ints_all, nmpc_peers** out)
+{
+    if (!out || world < 1 || world > nmpc::MAX_PEERS + 1 || rank < 0 || rank >= world || z_bytes_all == 0)
+        return fail(NMPC_ERR_ARG, "bad argument: world=%d (at most %d) rank=%d", world, nmpc::MAX_PEERS + 1, rank);
+    nmpc_peers* p = new nmpc_peers;
+    p->rank = rank; p->world = world;
+    p->z_bytes = z_bytes_all; p->info_ints = info_ints_all;
+    p->z_off = PEER_HDR_BYTES;
+    p->info_off = p->z_off + ((z_bytes_all + 255) & ~(size_t)255);
+    p->total = p->info_off + ((info_ints_all * sizeof(int) + 255) & ~(size_t)255);
+    void* mem = nullptr;
+    // plain cudaMalloc: the allocation has to be exportable by cudaIpcGetMemHandle (no pool / VMM memory)
+    if (cudaGetDevice(&p->device) != cudaSuccess || cudaMalloc(&mem, p->total) != cudaSuccess || cudaMemset(mem, 0, PEER_HDR_BYTES) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        if (mem) cudaFree(mem);
+        delete p;
+        return fail(NMPC_ERR_CUDA, "peer buffer allocation failed: %s", cudaGetErrorString(e));
+    }
+    p->base[rank] = static_cast<char*>(mem);
+    p->connected = (world == 1);
+    *out = p;
+    return 0;
+}
+int nmpc_peers_export(nmpc_peers* p, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    if (!p || !handle) return fail(NMPC_ERR_ARG, "null pointer argument");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, p->base[p->rank]));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+int nmpc_peers_connect(nmpc_peers* p, const unsigned char* handles)
+{
+    if (!p || !handles) return fail(NMPC_ERR_ARG, "null pointer argument");
+    if (p->connected) return fail(NMPC_ERR_ARG, "already connected");
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * 64, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; q++)
+                if (q != p->rank && p->base[q]) { cudaIpcCloseMemHandle(p->base[q]); p->base[q] = nullptr; }
+            return fail(NMPC_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (peers must be GPUs of one node with P2P access)", r,
+                        cudaGetErrorString(e));
+        }
+        p->base[r] = static_cast<char*>(ptr);
+    }
+    p->connected = true;
+    return 0;
+}
+void* nmpc_peers_z(nmpc_peers* p) { return p ? p->base[p->rank] + p->z_off : nullptr; }
+int* nmpc_peers_info(nmpc_peers* p) { return p ? reinterpret_cast<int*>(p->base[p->rank] + p->info_off) : nullptr; }
+int nmpc_peers_rank(const nmpc_peers* p) { return p ? p->rank : -1; }
+int nmpc_peers_world(const nmpc_peers* p) { return p ? p->world : -1; }
+int nmpc_peers_barrier(nmpc_peers* p, void* cuda_stream)
+{
+    if (!p) return fail(NMPC_ERR_ARG, "null pointer argument");
+    if (!p->connected) return fail(NMPC_ERR_ARG, "nmpc_peers_connect has not been called");
+    if (p->world == 1) return 0;
+    PeerSync ps;
+    for (int r = 0; r < p->world; r++) ps.hdr[r] = reinterpret_cast<unsigned*>(p->base[r]);
+    ps.rank = p->rank; ps.world = p->world;
+    peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(ps);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int nmpc_peers_status(nmpc_peers* p)
+{
+    if (!p) return fail(NMPC_ERR_ARG, "null pointer argument");
+    unsigned st = 0;
+    CUDA_TRY(cudaMemcpy(&st, p->base[p->rank] + PEER_STATUS * sizeof(unsigned), sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (st) return fail(NMPC_ERR_CUDA, "a peer did not reach the barrier within 2 s: the collated results are incomplete");
+    return 0;
+}
+int nmpc_peers_destroy(nmpc_peers* p)
+{
+    if (!p) return 0;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; r++)
+        if (r != p->rank && p->base[r]) cudaIpcCloseMemHandle(p->base[r]);
+    if (p->base[p->rank]) cudaFree(p->base[p->rank]);
+    delete p;
+    return 0;
+}
+
+static int solve_sharded_p2p(nmpc_peers* p, int B_local, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
+                             const int* nrows, int variant, const nmpc_opts* opts, void* info_real_local, void* stream, size_t esz, int mode)
+{
+    if (!p) return fail(NMPC_ERR_ARG, "null pointer argument");
+    if (!p->connected) return fail(NMPC_ERR_ARG, "nmpc_peers_connect has not been called");
+    if (B_local < 0 || mode < 0 || mode > 2 || (esz == 4 && mode == 0)) return fail(NMPC_ERR_ARG, "bad argument: B_local=%d mode=%d", B_local, mode);
+    const size_t zb = (size_t)B_local * N * 17 * esz, ib = (size_t)B_local * 4;
+    if ((zb & 15) != 0) return fail(NMPC_ERR_ARG, "B_local must keep every rank's slice 16-byte aligned (even B_local)");
+    if (zb * p->world > p->z_bytes || ib * p->world > p->info_ints)
+        return fail(NMPC_ERR_ARG, "collation buffers too small: %zu bytes of z for %d ranks x %d problems", p->z_bytes, p->world, B_local);
+    nmpc::PeerOut po;
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank) continue;
+        po.z[po.n] = p->base[r] + p->z_off + (size_t)p->rank * zb;
+        po.info[po.n] = reinterpret_cast<int*>(p->base[r] + p->info_off) + (size_t)p->rank * ib;
+        po.n++;
+    }
+    char* z_mine = p->base[p->rank] + p->z_off + (size_t)p->rank * zb;
+    int* ii_mine = reinterpret_cast<int*>(p->base[p->rank] + p->info_off) + (size_t)p->rank * ib;
+    // barrier 1: every rank has finished reading the previous batch's results (its readers precede this call on its
+    // stream), so the peers may be overwritten; barrier 2: every rank's results have landed everywhere
+    if (int rc = nmpc_peers_barrier(p, stream)) return rc;
+    int rc = mode == 0 ? solve_device(B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_mine, ii_mine, info_real_local, stream,
+                                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, &po)
+                       : solve_mixed(B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, z_mine, ii_mine, info_real_local, stream,
+                                     esz == 4, nullptr, nullptr, nullptr, nullptr, nullptr, mode == 2, &po);
+    if (rc) return rc;
+    return nmpc_peers_barrier(p, stream);
+}
+int nmpc_solve_batch_sharded_p2p_f64(nmpc_peers* peers, int B_local, int N, int mcap, const double* xinit, const double* z0,
+                                     const double* hdr, const double* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                                     double* info_real_local, int mode, void* cuda_stream)
+{
+    return solve_sharded_p2p(peers, B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, info_real_local, cuda_stream, 8, mode);
+}
+int nmpc_solve_batch_sharded_p2p_f32(nmpc_peers* peers, int B_local, int N, int mcap, const float* xinit, const float* z0,
+                                     const float* hdr, const float* rows, const int* nrows, int variant, const nmpc_opts* opts,
+                                     float* info_real_local, void* cuda_stream)
+{
+    return solve_sharded_p2p(peers, B_local, N, mcap, xinit, z0, hdr, rows, nrows, variant, opts, info_real_local, cuda_stream, 4, 1);
 }
 
 int nmpc_backsolve_factor_words(void) { return nmpc::FAC_WORDS; }

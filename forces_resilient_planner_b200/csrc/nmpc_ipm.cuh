@@ -39,6 +39,17 @@ struct Opts {
     int maxit, max_bt, pc, mixed;
 };
 
+// Multi-GPU collation by peer stores (nmpc_peers_* of the C ABI): base pointers of THIS rank's slice inside every other
+// rank's copy of the collation buffers, mapped into this process by CUDA IPC.  The epilogue of a solve writes the
+// solution and the four info integers to its own buffers and to all of these, so the exchange rides along with the
+// compute (NVLink stores spread over the whole kernel) and nothing is left to gather afterwards but a barrier.
+constexpr int MAX_PEERS = 15;
+struct PeerOut {
+    int n = 0;
+    void* z[MAX_PEERS];
+    int* info[MAX_PEERS];
+};
+
 // Problem data and results are arrays of T in HBM, or -- io32, fp64 kernel only: the re-solve of the
 // problems the mixed-precision kernel gave up on (nmpc_ipm_mixed.cuh) -- arrays of float.
 template <typename T> struct Params {
@@ -60,6 +71,7 @@ template <typename T> struct Params {
     void* zl_out;         // [B][N][17]  lower-bound multipliers
     void* zu_out;         // [B][N][17]  upper-bound multipliers
     void* lc_out;         // [B][N][mcap] corridor multipliers
+    PeerOut peers;        // n = 0: single GPU
     Opts o;
 };
 
@@ -194,13 +206,37 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// TMA 1-D bulk copy shared -> global
-__device__ __forceinline__ void tma_store(void* dst, const void* src, uint32_t bytes)
+// The solution [nz] and the info integers of problem b to this GPU's arrays and to every peer's (PeerOut).  NT threads of
+// the CTA take part (tid); fp64 results leave shared memory by TMA bulk stores (one per destination, one commit group),
+// float results (io32) by coalesced stores of the converted values.
+template <int NT, typename T>
+__device__ __forceinline__ void store_solution(const PeerOut& po, void* z_out, int* info_int, size_t b, const T* Zs, int nz, bool io32,
+                                               int tid, int flag, int it, int nbt, int resolved)
 {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (io32) {
+        for (int e = tid; e < nz; e += NT) {
+            const float v = (float)Zs[e];
+            static_cast<float*>(z_out)[b * nz + e] = v;
+            for (int p = 0; p < po.n; p++) static_cast<float*>(po.z[p])[b * nz + e] = v;
+        }
+    } else if (tid == 0) {
+        const uint32_t bytes = (uint32_t)nz * sizeof(T);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(static_cast<T*>(z_out) + b * nz), "r"(smem_u32(Zs)),
+                     "r"(bytes)
+                     : "memory");
+        for (int p = 0; p < po.n; p++)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(static_cast<T*>(po.z[p]) + b * nz),
+                         "r"(smem_u32(Zs)), "r"(bytes)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (tid == 0) {
+        int* ii = info_int + b * 4;
+        ii[0] = flag; ii[1] = it; ii[2] = nbt; ii[3] = resolved;
+        for (int p = 0; p < po.n; p++) *reinterpret_cast<int4*>(po.info[p] + b * 4) = make_int4(flag, it, nbt, resolved);
+    }
 }
 
 // 1/sqrt(x) and 1/x in double precision from the SFU's double-precision seeds (rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64:
@@ -1366,14 +1402,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const Params<T> prm)
     auto put = [&](void* base, size_t idx, T v) {
         if (io32) static_cast<float*>(base)[idx] = (float)v; else static_cast<T*>(base)[idx] = v;
     };
-    if (io32) {
-        for (int e = lane; e < N * NZ; e += 32) put(prm.z_out, (size_t)b * N * NZ + e, s.Z[e]);
-    } else if (lane == 0) {
-        tma_store(static_cast<T*>(prm.z_out) + (size_t)b * N * NZ, s.Z, bytes_z);
-    }
+    store_solution<32>(prm.peers, prm.z_out, prm.info_int, (size_t)b, s.Z, N * NZ, io32, lane, flag, it, nbt_total, prm.count ? 1 : 0);
     if (lane == 0) {
-        int* ii = prm.info_int + (size_t)b * 4;
-        ii[0] = flag; ii[1] = it; ii[2] = nbt_total; ii[3] = prm.count ? 1 : 0;
         const T v[8] = {req_n, rin_n, rs_n, rcomp, f_cur, mu, alpha_p, alpha_d};
 #pragma unroll
         for (int q = 0; q < 8; q++) put(prm.info_real, (size_t)b * 8 + q, v[q]);

@@ -710,14 +710,8 @@ __global__ void __launch_bounds__(GROUP_THREADS) nmpc_ipm_group_kernel(const Mix
     auto put = [&](void* base, size_t idx, double v) {
         if (io32) static_cast<float*>(base)[idx] = (float)v; else static_cast<double*>(base)[idx] = v;
     };
-    if (io32) {
-        for (int e = tid; e < N * NZ; e += NT) put(prm.z_out, (size_t)b * N * NZ + e, s.Z[e]);
-    } else if (tid == 0) {
-        tma_store(static_cast<double*>(prm.z_out) + (size_t)b * N * NZ, s.Z, N * NZ * 8);
-    }
+    store_solution<NT>(prm.peers, prm.z_out, prm.info_int, (size_t)b, s.Z, N * NZ, io32, tid, flag, it, nbt_total, 0);
     if (tid == 0) {
-        int* ii = prm.info_int + (size_t)b * 4;
-        ii[0] = flag; ii[1] = it; ii[2] = nbt_total; ii[3] = 0;
         const double v[8] = {req_n, rin_n, rs_n, rcomp, f_cur, mu, alpha_p, alpha_d};
 #pragma unroll
         for (int q = 0; q < 8; q++) put(prm.info_real, (size_t)b * 8 + q, v[q]);

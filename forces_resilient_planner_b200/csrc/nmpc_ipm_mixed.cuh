@@ -46,6 +46,7 @@ struct MixedParams {
     int* info_int;        // [B][4]  exitflag, iterations, backtracks, 0 (1 = re-solved by the fp64 kernel)
     void* info_real;      // [B][8]
     void *y_out, *zl_out, *zu_out, *lc_out;   // optional multipliers, same element type as the problem data
+    PeerOut peers;        // multi-GPU collation by peer stores (nmpc_ipm.cuh); n = 0: single GPU
     Opts o;
 };
 
@@ -538,15 +539,8 @@ __global__ void __launch_bounds__(32) nmpc_ipm_mixed_kernel(const MixedParams pr
 
     // ---- results -----------------------------------------------------------------------------
     __syncwarp();
-    if (io32) {
-        float* zo = static_cast<float*>(prm.z_out) + (size_t)b * N * NZ;
-        for (int e = lane; e < N * NZ; e += 32) zo[e] = (float)s.Z[e];
-    } else if (lane == 0) {
-        tma_store(static_cast<double*>(prm.z_out) + (size_t)b * N * NZ, s.Z, N * NZ * 8);
-    }
+    store_solution<32>(prm.peers, prm.z_out, prm.info_int, (size_t)b, s.Z, N * NZ, io32, lane, flag, it, nbt_total, 0);
     if (lane == 0) {
-        int* ii = prm.info_int + (size_t)b * 4;
-        ii[0] = flag; ii[1] = it; ii[2] = nbt_total; ii[3] = 0;
         const double v[8] = {req_n, rin_n, rs_n, rcomp, f_cur, mu, alpha_p, alpha_d};
 #pragma unroll
         for (int q = 0; q < 8; q++) {

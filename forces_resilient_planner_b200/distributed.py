@@ -7,6 +7,10 @@ into its slice of ONE buffer of world*per problems and an in-place all-gather (s
 same stream completes the other slices -- `nmpc_solve_batch_sharded_{f64,f32}` of the C ABI (include/nmpc_b200.h), which
 drives NCCL itself.  torch.distributed is used for one thing only: handing rank 0's 128-byte NCCL id to the other ranks.
 
+`PeerCollator` goes one step further on the GPUs of one node (`nmpc_solve_batch_sharded_p2p_*`): the solve kernel's epilogue
+writes every result into all ranks' buffers over NVLink (CUDA IPC mappings), so the exchange overlaps the arithmetic and
+only a barrier kernel follows the solve.
+
 `TorchCollator` is the same in-place gather through torch.distributed (any backend): it exists so that the host logic
 (shard arithmetic, slice placement, trimming of the padded tail) is testable with `gloo` on CPU, world size 2.
 """
@@ -91,15 +95,7 @@ class NcclCollator:
         with torch.cuda.device(self.device):
             _check(self.lib.nmpc_comm_alloc(self.comm, n, ctypes.byref(ptr)))
         self._bufs.append(ptr)
-        np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32}[dtype]
-
-        class _Mem:      # __cuda_array_interface__: torch wraps the memory without copying
-            pass
-        m = _Mem()
-        m.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=np.dtype(np_dt).str, data=(ptr.value, False), version=3)
-        t = torch.as_tensor(m, device=self.device)
-        t._nmpc_owner = self          # keeps the communicator (and with it the allocation) alive
-        return t
+        return _wrap_device_memory(torch, ptr.value, shape, dtype, self.device, self)   # keeps the communicator alive
 
     def solve_sharded(self, db, z_all, info_int_all, opts=None, mixed: bool = False, stream=None):
         """Enqueue solve + in-place all-gather for this rank's DeviceBatch `db` (every rank: the same db.B)."""
@@ -128,6 +124,95 @@ class NcclCollator:
             self.torch.cuda.synchronize(self.device)
             self.lib.nmpc_comm_destroy(self.comm)
             self.comm = ctypes.c_void_p()
+
+
+def _wrap_device_memory(torch, ptr: int, shape, dtype, device, owner):
+    """A torch tensor over device memory this library owns (no copy; `owner` is kept alive by the tensor)."""
+    np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32}[dtype]
+
+    class _Mem:      # __cuda_array_interface__
+        pass
+    m = _Mem()
+    m.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=np.dtype(np_dt).str, data=(int(ptr), False), version=3)
+    t = torch.as_tensor(m, device=device)
+    t._nmpc_owner = owner
+    return t
+
+
+class PeerCollator:
+    """nmpc_peers of the C ABI: collation by peer stores from inside the solve kernel (GPUs of one node).
+
+    Every rank holds z_all [world * per][N][17] and info_all [world * per][4]; the solve kernel of rank r writes its
+    results into slice r of every rank's copy, two barrier kernels bracket the solve.  torch.distributed (any backend)
+    is used once, to exchange the 64-byte CUDA IPC handles."""
+
+    def __init__(self, rank: int, world: int, device, per: int, N: int, dtype=np.float64, group=None, handles=None):
+        import torch
+        self.torch, self.lib = torch, _lib.load()
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.per, self.N, self.np_dtype = per, N, np.dtype(dtype)
+        lib = self.lib
+        vp, i = ctypes.c_void_p, ctypes.c_int
+        lib.nmpc_peers_create.argtypes = [i, i, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(vp)]
+        lib.nmpc_peers_export.argtypes = [vp, ctypes.c_char_p]
+        lib.nmpc_peers_connect.argtypes = [vp, ctypes.c_char_p]
+        lib.nmpc_peers_z.argtypes = [vp]; lib.nmpc_peers_z.restype = vp
+        lib.nmpc_peers_info.argtypes = [vp]; lib.nmpc_peers_info.restype = vp
+        for name in ("nmpc_peers_status", "nmpc_peers_destroy"):
+            getattr(lib, name).argtypes = [vp]
+        lib.nmpc_peers_barrier.argtypes = [vp, vp]
+        sig = [vp, i, i, i] + [vp] * 5 + [i, ctypes.POINTER(_lib.NmpcOpts), vp]
+        lib.nmpc_solve_batch_sharded_p2p_f64.argtypes = sig + [i, vp]
+        lib.nmpc_solve_batch_sharded_p2p_f32.argtypes = sig + [vp]
+        self.peers = vp()
+        zbytes = world * per * N * 17 * self.np_dtype.itemsize
+        with torch.cuda.device(self.device):
+            _check(lib.nmpc_peers_create(world, rank, zbytes, world * per * 4, ctypes.byref(self.peers)))
+            if world > 1:
+                if handles is None:
+                    import torch.distributed as dist
+                    mine = ctypes.create_string_buffer(64)
+                    _check(lib.nmpc_peers_export(self.peers, mine))
+                    box = [None] * world
+                    dist.all_gather_object(box, mine.raw, group=group)
+                    handles = b"".join(box)
+                _check(lib.nmpc_peers_connect(self.peers, handles))
+        t_dt = torch.float64 if self.np_dtype == np.float64 else torch.float32
+        self.z_all = _wrap_device_memory(torch, lib.nmpc_peers_z(self.peers), (world * per, N, 17), t_dt, self.device, self)
+        self.info_all = _wrap_device_memory(torch, lib.nmpc_peers_info(self.peers), (world * per, 4), torch.int32, self.device, self)
+
+    def solve_sharded(self, db, opts=None, mode: int = 0, stream=None):
+        """Enqueue barrier + solve with peer stores + barrier for this rank's DeviceBatch (db.B == per on every rank).
+        mode: 0 fp64 kernel, 1 mixed precision, 2 low-latency warp-group kernel."""
+        torch = self.torch
+        assert db.B == self.per and db.N == self.N and db.np_dtype == self.np_dtype
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        o = opts or _lib.default_opts()
+        d = db.d
+        args = [self.peers, db.B, db.N, db.mcap, d["xinit"].data_ptr(), d["z0"].data_ptr(), d["hdr"].data_ptr(),
+                d["rows"].data_ptr(), d["nrows"].data_ptr(), db.variant, ctypes.byref(o), db.info_real.data_ptr()]
+        with torch.cuda.device(self.device):
+            if self.np_dtype == np.float32:
+                _check(self.lib.nmpc_solve_batch_sharded_p2p_f32(*args, ctypes.c_void_p(st.cuda_stream)))
+            else:
+                _check(self.lib.nmpc_solve_batch_sharded_p2p_f64(*args, int(mode), ctypes.c_void_p(st.cuda_stream)))
+
+    def barrier(self, stream=None):
+        st = stream if stream is not None else self.torch.cuda.current_stream(self.device)
+        with self.torch.cuda.device(self.device):
+            _check(self.lib.nmpc_peers_barrier(self.peers, ctypes.c_void_p(st.cuda_stream)))
+
+    def check(self):
+        """Synchronous: raises if a barrier timed out (a rank missing for 2 s)."""
+        with self.torch.cuda.device(self.device):
+            _check(self.lib.nmpc_peers_status(self.peers))
+
+    def close(self):
+        """Call on every rank after a host-level barrier: no peer may still be writing into this rank's buffers."""
+        if self.peers:
+            with self.torch.cuda.device(self.device):
+                self.lib.nmpc_peers_destroy(self.peers)
+            self.peers = ctypes.c_void_p()
 
 
 class TorchCollator:

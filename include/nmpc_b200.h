@@ -195,6 +195,40 @@ int nmpc_solve_batch_sharded_f32(nmpc_comm *comm, int B_local, int N, int mcap, 
                                  float *info_real_local, void *cuda_stream);
 int nmpc_collate_inplace(nmpc_comm *comm, void *buf_all, size_t bytes_per_rank, void *cuda_stream);
 
+/* ---- multi-GPU, fused: collation by peer stores from inside the solve kernel (GPUs of one node, NVLink / NVSwitch) --
+ * Every rank owns one allocation [header | z_all | info_int_all] (nmpc_peers_create) and maps the allocation of every
+ * other rank (CUDA IPC: nmpc_peers_export -> the application exchanges the 64-byte handles the way it exchanges the
+ * NCCL id -> nmpc_peers_connect).  The epilogue of the solve kernel then writes each problem's solution and info
+ * integers into its slice of EVERY rank's buffers (TMA bulk stores to peer addresses), so the exchange is spread over
+ * the whole kernel and overlaps the arithmetic; what remains of the collation is a barrier kernel on the same stream
+ * (release/acquire flags in the peers' headers, epoch kept on the device: CUDA-graph safe).
+ *   nmpc_solve_batch_sharded_p2p_f64 / _f32
+ *       barrier (every rank is done reading the previous batch) -> solve with peer stores -> barrier (all results
+ *       have landed everywhere).  mode: 0 fp64 kernel, 1 mixed precision, 2 low-latency warp-group kernel; _f32 is
+ *       always mixed.  Results: nmpc_peers_z() [world * B_local][N][17], nmpc_peers_info() [world * B_local][4] on
+ *       every rank.  Every rank must call with the same B_local (even) the same number of times.
+ *   nmpc_peers_status   synchronous; non-zero if a barrier timed out (a rank missing for 2 s)
+ *   nmpc_peers_destroy  the application synchronises the ranks first (no peer may still be writing)
+ * No NCCL involved.  Across nodes, or without P2P access, use nmpc_solve_batch_sharded_* above.              */
+typedef struct nmpc_peers nmpc_peers;
+int nmpc_peers_create(int world, int rank, size_t z_bytes_all, size_t info_ints_all, nmpc_peers **peers);
+int nmpc_peers_export(nmpc_peers *peers, unsigned char handle[64]);
+int nmpc_peers_connect(nmpc_peers *peers, const unsigned char *handles /* [world][64], own entry ignored */);
+void *nmpc_peers_z(nmpc_peers *peers);
+int *nmpc_peers_info(nmpc_peers *peers);
+int nmpc_peers_rank(const nmpc_peers *peers);
+int nmpc_peers_world(const nmpc_peers *peers);
+int nmpc_peers_barrier(nmpc_peers *peers, void *cuda_stream);
+int nmpc_peers_status(nmpc_peers *peers);
+int nmpc_peers_destroy(nmpc_peers *peers);
+int nmpc_solve_batch_sharded_p2p_f64(nmpc_peers *peers, int B_local, int N, int mcap, const double *xinit,
+                                     const double *z0, const double *hdr, const double *rows, const int *nrows,
+                                     int variant, const nmpc_opts *opts, double *info_real_local, int mode,
+                                     void *cuda_stream);
+int nmpc_solve_batch_sharded_p2p_f32(nmpc_peers *peers, int B_local, int N, int mcap, const float *xinit,
+                                     const float *z0, const float *hdr, const float *rows, const int *nrows,
+                                     int variant, const nmpc_opts *opts, float *info_real_local, void *cuda_stream);
+
 /* ---- stand-alone structured KKT factorisation / backsolve (device pointers) ------------------
  * The split the reference binary makes internally (f_17_PD_ldlchol_rowmajor ... vs
  * f_17_ldl_forward_solve_rm / f_13_backward_solve_rm) for the Riccati factor:

@@ -4,5 +4,5 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --mast
 python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/r02_bench_8gpu.json') if l.startswith('{')][-1])
-for k in ("value","e2e","collate","config4","config5"): print(k, json.dumps(d.get(k))[:1200])
+for k in ("value","e2e","collate","config4","config5"): print(k, json.dumps(d.get(k))[:1600])
 PY
