@@ -306,7 +306,7 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     // i+1 and the D2H copy of chunk i-1 overlap the solve of chunk i, and the next chunk's CTAs fill
     // the tail wave of the previous kernel.  Chunk boundaries are multiples of 4 problems, so every
     // per-problem block keeps the 16-byte alignment the TMA copies need (fp32 and fp64).
-    const int n_chunks = B >= 2048 ? 4 : 1;
+    const int n_chunks = B >= 4096 ? 8 : (B >= 2048 ? 4 : 1);
     const int per = ((B + n_chunks - 1) / n_chunks + 3) & ~3;
     auto enqueue = [&]() -> int {
         for (int c = 0, lo = 0; lo < B; c++, lo += per) {
