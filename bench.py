@@ -143,6 +143,43 @@ def cpu_single_thread_latency():
     return out
 
 
+def gpu_single_solve_latency():
+    """The reference's own use: ONE vehicle, one FORCESNLPsolver_normal_solve call per replan (host structs in, host structs
+    out: packing, H2D, solve, D2H inside the timer).  Same instances as cpu_single_thread_latency(); per kernel choice of
+    the shim (NMPC_B200_SHIM)."""
+    from forces_resilient_planner_b200 import forces, workloads as W
+    out = {}
+    b1, b2 = W.config1(), W.config2(1000)
+    saved = os.environ.get("NMPC_B200_SHIM")
+    try:
+        for name, env in (("warp_group_default", None), ("fp64_one_warp", "fp64")):
+            if env is None:
+                os.environ.pop("NMPC_B200_SHIM", None)
+            else:
+                os.environ["NMPC_B200_SHIM"] = env
+            w = forces.FORCESNormal()
+            rec = {}
+            for label, batch, idx in (("config1_x200", b1, [0] * 203), ("config2_200_instances", b2, list(range(203)))):
+                ts, ok = [], 0
+                for n, i in enumerate(idx):
+                    xinit, x0, allp = W.to_forces_params(batch, i)
+                    w.params_.xinit[:] = xinit.tolist(); w.params_.x0[:] = x0.tolist(); w.params_.all_parameters[:] = allp.tolist()
+                    t0 = time.perf_counter()
+                    flag = w.solve_params()
+                    dt = time.perf_counter() - t0
+                    if n >= 3:                                   # first calls: context, arena, streams
+                        ts.append(dt * 1e3); ok += int(flag == 1)
+                rec[label] = {**pct(np.array(ts)), "converged_frac": ok / len(ts)}
+            out[name] = rec
+    finally:
+        if saved is None:
+            os.environ.pop("NMPC_B200_SHIM", None)
+        else:
+            os.environ["NMPC_B200_SHIM"] = saved
+    out["unit"] = "ms per FORCESNLPsolver_normal_solve call (host structs in / out), cold starts"
+    return out
+
+
 def reference_binary_attempt():
     """one real call of the reference's solver archive (oracle/_ref/forces_attempt, linked
     in the build container against SOLN/FORCESNLPsolver_normal/lib/libFORCESNLPsolver_normal.a where it lies)."""
@@ -428,6 +465,7 @@ def run_b200(args):
                     "round-1 Schur restatement the ratio was ~6x larger -- that CPU arm did ~3x the flops per iteration plus refinement",
             "single_thread_ms": cpu_single_thread_latency(),
             "reference_binary_attempt": reference_binary_attempt()}
+        extras["single_solve_ms"] = gpu_single_solve_latency()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -14,6 +14,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -120,6 +121,31 @@ int launch_group(const nmpc::MixedParams& prm, cudaStream_t st)
     return 0;
 }
 
+// Stream-ordered scratch memory comes from the library's OWN pool (one per device) that keeps what it has been given: the
+// default pool returns freed memory to the driver at the next synchronisation, which turns every small solve into a
+// cudaMalloc / cudaFree pair (milliseconds).  The process-wide default pool's settings are not touched.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pool[kMaxDevices] = {};
+int scratch_pool(cudaMemPool_t* out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(NMPC_ERR_CUDA, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        CUDA_TRY(cudaMemPoolCreate(&g_pool[dev], &props));
+        uint64_t keep = UINT64_MAX;
+        CUDA_TRY(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *out = g_pool[dev];
+    return 0;
+}
+
 // order[0 .. *count) <- the problems whose exit flag is not 1 (optimal); one pass, order of arrival
 __global__ void collect_unsolved_kernel(int B, const int* info_int, int* count, int* order)
 {
@@ -195,7 +221,9 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
                        : (N == 20 ? launch_mixed<20>(prm, st) : launch_mixed<40>(prm, st))) return rc;
     if (o.mixed < 0) return 0;                      // opts.mixed = -1: no fp64 safety net (tests, profiling)
     int* ws = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), ((size_t)B + 4) * sizeof(int), st));
+    cudaMemPool_t pool;
+    if (int rc = scratch_pool(&pool)) return rc;
+    CUDA_TRY(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws), ((size_t)B + 4) * sizeof(int), pool, st));
     CUDA_TRY(cudaMemsetAsync(ws, 0, 4 * sizeof(int), st));
     collect_unsolved_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, info_int, ws, ws + 4);
     CUDA_TRY(cudaGetLastError());
@@ -278,7 +306,7 @@ inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 // esz = 4: float arrays, mixed-precision kernel.
 int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const void* hdr, const void* rows,
                const int* nrows, int variant, const nmpc_opts* opts, void* z_out, int* info_int, void* info_real,
-               size_t esz, bool mixed)
+               size_t esz, bool mixed, bool group = false)
 {
     if (B < 0) return fail(NMPC_ERR_ARG, "B < 0");
     if (B == 0) return 0;
@@ -324,7 +352,7 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
             if (mixed)
                 rc = solve_mixed(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
                                  reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
-                                 base + o_ir + lo * pir, st, esz == 4);
+                                 base + o_ir + lo * pir, st, esz == 4, nullptr, nullptr, nullptr, nullptr, nullptr, group);
             else
                 rc = solve_device(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
                                   reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
@@ -452,8 +480,13 @@ int forces_solve(const double* xinit, const double* x0, const double* allp, doub
         }
     }
     int ii[4] = {0, 0, 0, 0};
+    // One vehicle, one solve: what counts is the latency of that solve, so the default is the warp-group kernel (256
+    // threads on the one problem, mixed precision at the reference tolerances, fp64 safety net on the same stream).
+    // NMPC_B200_SHIM=fp64 selects the one-warp fp64 kernel, =mixed the one-warp mixed-precision kernel.
+    const char* sel = std::getenv("NMPC_B200_SHIM");
+    const bool fp64 = sel && std::strcmp(sel, "fp64") == 0, warp = sel && std::strcmp(sel, "mixed") == 0;
     int rc = solve_host(1, N, mcap, xinit, x0, hdr.data(), rows.data(), nrows.data(), variant, nullptr,
-                        out340, ii, ir, sizeof(double), false);
+                        out340, ii, ir, sizeof(double), !fp64, !fp64 && !warp);
     *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     // inequalities of the problem as solved: two bound sides per free variable + the live corridor rows of stages 1..N-1
     *n_ineq = 2 * (8 + (N - 1) * 17);

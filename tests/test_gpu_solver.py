@@ -123,8 +123,23 @@ def test_full_size_config2_properties():
     assert np.max(np.abs(g2.z - g.z)) < 5e-3 and np.median(np.abs(g2.z - g.z).reshape(b.B, -1).max(1)) < 1e-4
 
 
-def test_forces_abi_shim_matches_batch_api():
+# The reference symbols run one solve at a time: by default on the warp-group kernel (mixed precision at the reference
+# tolerances: within 1e-3 of the fp64 KKT point, SURVEY 8c pin 4), with NMPC_B200_SHIM=fp64 on the one-warp fp64 kernel
+# (then bit-identical to the batched fp64 entry points).
+SHIM_MODES = [("fp64", 1e-12, 1e-9, 0), ("mixed", 1e-3, 1e-3, 1), (None, 1e-3, 1e-3, 1)]
+
+
+def _set_shim(monkeypatch, mode):
+    if mode is None:
+        monkeypatch.delenv("NMPC_B200_SHIM", raising=False)
+    else:
+        monkeypatch.setenv("NMPC_B200_SHIM", mode)
+
+
+@pytest.mark.parametrize("mode,tol,tol9,dit", SHIM_MODES)
+def test_forces_abi_shim_matches_batch_api(monkeypatch, mode, tol, tol9, dit):
     """FORCESNLPsolver_normal_solve / _final_solve with the reference's padded 130-slot layout."""
+    _set_shim(monkeypatch, mode)
     for variant, cls in ((0, forces.FORCESNormal), (1, forces.FORCESFinal)):
         b = W.config2(3, variant=variant)
         ref = S.solve_host(b)
@@ -135,13 +150,16 @@ def test_forces_abi_shim_matches_batch_api():
             w.params_.all_parameters[:] = allp.tolist()
             flag = w.solve_params()
             assert flag == 1 == ref.flag[i]
-            assert np.max(np.abs(w.output_array() - ref.z[i])) < 1e-12
-            assert w.info_.it == ref.it[i] and w.info_.solvetime > 0
-            assert abs(w.info_.pobj - ref.info_real[i, 4]) < 1e-12 and w.info_.rsnorm <= TOL
+            assert np.max(np.abs(w.output_array() - ref.z[i])) < tol
+            assert abs(w.info_.it - ref.it[i]) <= dit and w.info_.solvetime > 0
+            assert abs(w.info_.pobj - ref.info_real[i, 4]) < max(tol, 1e-12) * max(1.0, abs(ref.info_real[i, 4]))
+            assert max(w.info_.rsnorm, w.info_.res_eq, w.info_.res_ineq, w.info_.rcompnorm) <= TOL
 
 
-def test_reference_wrapper_flow_solveNormal_updateNormal():
+@pytest.mark.parametrize("mode,tol,tol9,dit", SHIM_MODES)
+def test_reference_wrapper_flow_solveNormal_updateNormal(monkeypatch, mode, tol, tol9, dit):
     """The planner's own call sequence (nmpc_solver.cpp:384,421): setParas -> solve -> update."""
+    _set_shim(monkeypatch, mode)
     b = W.config1()
     w = forces.FORCESNormal()
     w.setParasNormal(7.0, 1.0, 80.0, 12.0, 0.5)
@@ -153,7 +171,7 @@ def test_reference_wrapper_flow_solveNormal_updateNormal():
     assert flag == 1
     w.updateNormal(mpc_output)
     direct = S.solve_host(b)
-    assert np.max(np.abs(np.array(mpc_output[:20]) - direct.z[0])) < 1e-9
+    assert np.max(np.abs(np.array(mpc_output[:20]) - direct.z[0])) < tol9
 
 
 def test_edge_cases_rows_and_batch_sizes():
@@ -611,10 +629,12 @@ def test_scheduling_order_does_not_change_results():
     assert np.array_equal(z.cpu().numpy(), ref.z) and np.array_equal(ii.cpu().numpy()[:, 1], ref.it)
 
 
-def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows():
+@pytest.mark.parametrize("mode,tol,tol9,dit", SHIM_MODES)
+def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows(monkeypatch, mode, tol, tol9, dit):
     """The reference layout allows 30 rows per stage; DecompROS polytopes can also leave zero rows in
     the middle once tightened rows are dropped upstream.  The shim compacts them; the result must
     equal the native batched call on the compacted problem."""
+    _set_shim(monkeypatch, mode)
     rng = np.random.default_rng(4)
     b = W.config3(2, mcap=30)
     w = forces.FORCESNormal()
@@ -642,7 +662,7 @@ def test_forces_shim_with_full_30_row_corridors_and_interleaved_zero_rows():
                 rows[0, k, q, 0:3] = allp[k, 10 + 3 * j:13 + 3 * j]; rows[0, k, q, 3] = allp[k, 100 + j]
         nb = W.Batch(b.xinit[i:i + 1], b.z0[i:i + 1], b.hdr[i:i + 1], rows, nrows, 0)
         ref = S.solve_host(nb)
-        assert ref.flag[0] == 1 and np.max(np.abs(w.output_array() - ref.z[0])) < 1e-9
+        assert ref.flag[0] == 1 and np.max(np.abs(w.output_array() - ref.z[0])) < tol9
         # inactive far planes must not move the solution away from the original problem's
         base = S.solve_host(b.slice(i, i + 1))
         assert np.max(np.abs(base.z[0] - ref.z[0])) < 1e-4
