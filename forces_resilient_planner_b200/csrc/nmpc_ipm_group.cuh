@@ -55,7 +55,10 @@ template <int N> struct GLayout {
     static constexpr int SH_JC = SH_D + N * NXI;
     static constexpr int SH_PHID = SH_JC + N * NJC;
     static constexpr int SH_GF = SH_PHID + N * PHI_S;    // 13 x 14: F'(P+ F) and F' tv of the current stage
-    static constexpr int SH_END = SH_GF + 13 * 14 + 2;
+    static constexpr int SH_PK = SH_GF + 13 * 14 + 2;    // the cost-to-go matrices P_k of all stages (costates in one parallel step)
+    static constexpr int SH_AK = SH_PK + N * 169;        // closed-loop transition [A_k | b_k], 13 x 14 per stage (rollout)
+    static constexpr int SH_XI = SH_AK + N * 182;        // the rolled-out dxi_k, 13 per stage
+    static constexpr int SH_END = SH_XI + N * NXI + 3;
     static constexpr int STG_HDR_BYTES = N * NZ * 8;     // TMA staging (z0, then hdr) at SH_DZ
     __host__ __device__ static constexpr size_t bytes(int mcap)
     {
@@ -393,6 +396,105 @@ template <int N> struct GroupSolver {
         return (d.mA * a + d.mB * b) + d.cc * f32[d.xc];
     }
 
+    // ------------------------------------------------- forward rollout and costates, 256 threads ----
+    // The one-warp kernels roll the step out stage by stage (du_k = K_k dxi_k + kff_k, dxi_k+1 = d_k + M_k dxi_k + B_k du_k:
+    // a gain product, shuffles and a Jacobian product on the dependent chain, ~500 cycles per stage) and recover the
+    // costates by a second dependent sweep.  Here everything that does not depend on the rolled-out state is taken off the
+    // chain:
+    //   1. all threads, one (stage, row) each: the closed-loop transition A_k = M_k + B_k K_k, b_k = d_k + B_k kff_k
+    //      (M_k, B_k: the structured Jacobian blocks); warp 0 meanwhile solves stage 0 (dq_0 = -P_qq^-1 p_q);
+    //   2. warp 0: dxi_k+1 = b_k + A_k dxi_k, lane = row, the state passed by shuffles (13 multiply-adds per stage);
+    //   3. all threads: du_k = K_k dxi_k + kff_k and the step dz_k; costates y_k = P_k dxi_k + p_k from the stored
+    //      cost-to-go (p_k sits where y_k goes) -- both read only dxi, no barrier between them.
+    // Returns false (on warp 0) if the stage-0 block is not positive definite.
+    __device__ bool rollout_and_costates()
+    {
+        float* AK = f32 + GL::SH_AK;
+        float* XI = f32 + GL::SH_XI;
+        bool ok = true;
+        if (warp == 0) {                                             // stage 0: x fixed (dx = 0), u_prev free
+            const float* PN = f32 + L32::PN;
+            float a[16], l[10], li[4], x[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int c = 0; c <= r; c++) a[4 * r + c] = PN[(9 + r) * 13 + 9 + c];
+                x[r] = -DY[9 + r];
+            }
+            ok = chol4<float>(a, l, li);
+            fsub4<float>(l, li, x);
+            bsub4<float>(l, li, x);
+            if (lane < 13) XI[lane] = (lane < 9) ? 0.f : (lane == 9 ? x[0] : (lane == 10 ? x[1] : (lane == 11 ? x[2] : x[3])));
+        }
+        for (int t = tid; t < (N - 1) * NXI; t += NT) {
+            const int k = t / NXI, i = t - k * NXI;
+            const int rt = i < 3 ? 0 : (i < 6 ? 1 : (i < 9 ? 2 : 3));
+            const int r = i - (rt == 0 ? 0 : (rt == 1 ? 3 : (rt == 2 ? 6 : 9)));
+            const float* jc = JC + k * NJC;
+            const float* kg = sw.KG + k * 52;
+            const float* kff = sw.KFF + k * 4;
+            float b4[4];
+#pragma unroll
+            for (int c = 0; c < 3; c++) b4[c] = rt == 1 ? jc[JVW + 3 * r + c] : (rt >= 2 && c == r ? (rt == 2 ? (float)C::h : 1.f) : 0.f);
+            b4[3] = rt == 0 ? jc[JPT + r] : (rt == 1 ? jc[JVT + r] : (rt == 3 && r == 3 ? 1.f : 0.f));
+            const int offV = rt == 0 ? JPV + 3 * r : JVV + 3 * r, offR = rt == 0 ? JPR + 3 * r : JVR + 3 * r;
+            float* arow = AK + k * 182 + i * 14;
+#pragma unroll
+            for (int j = 0; j < NXI; j++) {
+                float m = 0.f;
+                if (j >= 3 && j < 6) m = rt <= 1 ? jc[offV + j - 3] : 0.f;
+                if (j >= 6 && j < 9) m = rt <= 1 ? jc[offR + j - 6] : 0.f;
+                if ((rt == 0 || rt == 2) && j == i) m += 1.f;
+                arow[j] = m + ((b4[0] * kg[j] + b4[1] * kg[13 + j]) + (b4[2] * kg[26 + j] + b4[3] * kg[39 + j]));
+            }
+            arow[13] = D[t] + ((b4[0] * kff[0] + b4[1] * kff[1]) + (b4[2] * kff[2] + b4[3] * kff[3]));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int row = lane < 13 ? lane : 0;
+            float xi = XI[row];
+            for (int k = 0; k < N - 1; k++) {
+                const float* arow = AK + k * 182 + row * 14;
+                float c0 = arow[13], c1 = 0.f, c2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 12; j += 3) {
+                    c0 += arow[j] * __shfl_sync(0xffffffffu, xi, j);
+                    c1 += arow[j + 1] * __shfl_sync(0xffffffffu, xi, j + 1);
+                    c2 += arow[j + 2] * __shfl_sync(0xffffffffu, xi, j + 2);
+                }
+                c0 += arow[12] * __shfl_sync(0xffffffffu, xi, 12);
+                xi = (c0 + c1) + c2;
+                if (lane < 13) XI[(k + 1) * NXI + lane] = xi;
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < N * NZ; t += NT) {
+            const int k = t / NZ, i = t - k * NZ;
+            const float* xk = XI + k * NXI;
+            float v;
+            if (i < 4) {
+                const float* kg = sw.KG + k * 52 + i * 13;
+                float c0 = sw.KFF[k * 4 + i], c1 = 0.f, c2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 12; j += 3) { c0 += kg[j] * xk[j]; c1 += kg[j + 1] * xk[j + 1]; c2 += kg[j + 2] * xk[j + 2]; }
+                v = (c0 + c1) + (c2 + kg[12] * xk[12]);
+            } else {
+                v = xk[i < 8 ? 5 + i : i - 8];
+            }
+            DZ[t] = v;
+        }
+        for (int t = NXI + tid; t < N * NXI; t += NT) {
+            const int k = t / NXI, i = t - k * NXI;
+            const float* pk = f32 + GL::SH_PK + k * 169 + i * 13;
+            const float* xk = XI + k * NXI;
+            float c0 = DY[t], c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; j += 3) { c0 += pk[j] * xk[j]; c1 += pk[j + 1] * xk[j + 1]; c2 += pk[j + 2] * xk[j + 2]; }
+            DY[t] = (c0 + c1) + (c2 + pk[12] * xk[12]);
+        }
+        return ok;
+    }
+
     __device__ bool riccati_backward()
     {
         constexpr int PN = L32::PN, PF = L32::PF, TV = L32::TV, QUU = L32::QUU, QUR = L32::QUR, QV = L32::QV, QXI = L32::QXI,
@@ -530,6 +632,8 @@ template <int N> struct GroupSolver {
                 v -= (ys[di] * ys[dj] + ys[13 + di] * ys[13 + dj]) + (ys[26 + di] * ys[26 + dj] + ys[39 + di] * ys[39 + dj]);
                 f32[PN + di * 13 + dj] = v;
                 f32[PN + dj * 13 + di] = v;
+                f32[GL::SH_PK + k * 169 + di * 13 + dj] = v;
+                f32[GL::SH_PK + k * 169 + dj * 13 + di] = v;
             } else if (dvec) {
                 const float* ys = f32 + YS;
                 const float* y0 = f32 + Y0;
@@ -668,16 +772,10 @@ __global__ void __launch_bounds__(GROUP_THREADS) nmpc_ipm_group_kernel(const Mix
         s.assemble(mu_t);
         __syncthreads();
         bool ok = s.riccati_backward();
-        if (s.warp == 0) {
-            ok &= s.sw.rollout();
-            s.sw.costates();
-        }
-        {   // every thread takes the same branch on the factorisation outcome (warp 0 holds the pivots' verdict)
-            __syncthreads();
-            if (tid == 0) s.RED[0] = ok ? 1.0 : 0.0;
-            __syncthreads();
-            ok = s.RED[0] != 0.0;
-        }
+        ok &= s.rollout_and_costates();
+        if (tid == 0) s.RED[0] = ok ? 1.0 : 0.0;         // warp 0 holds the pivots' verdict: every thread takes the same branch on it
+        __syncthreads();
+        ok = s.RED[0] != 0.0;
         if (!ok) { flag = -5; break; }
         const double tau = fmin(fmax(0.995, 1.0 - mu), 0.99999);
         double ap, ad;
