@@ -389,12 +389,10 @@ def run_b200(args):
                           "buffer; in-place ncclAllGather (z + info) on the same stream"}
 
         # ---- the same step with the exchange fused into the solve kernel: peer stores over NVLink + barrier kernels ----
-        try:
-            pc = D.PeerCollator(rank, world, dev, B, HORIZON)
-        except RuntimeError as e:
-            pc = None
-            collate = {"p2p_unavailable": str(e), **collate, "method": "nccl_allgather"}
-        if pc is not None:
+        pc, why = make_peer_collator(D, dist, torch, rank, world, dev, B, HORIZON, np.float64)
+        if pc is None:
+            collate = {"p2p_unavailable": why, **collate, "method": "nccl_allgather"}
+        else:
             p_ms = timed(lambda: pc.solve_sharded(db, opts), args.steps, max(args.warmup, 3))
             p_total = max_over_ranks(sum(p_ms) * 1e-3)
             barrier_ms = max_over_ranks(float(np.mean(timed(lambda: pc.barrier(), 10, 3))))
@@ -489,6 +487,23 @@ def run_b200(args):
     return 0
 
 
+def make_peer_collator(D, dist, torch, rank, world, dev, per, N, dtype):
+    """PeerCollator on every rank or on none: CUDA IPC needs the GPUs of one node with P2P access, and a rank that cannot
+    map its peers must not leave the others waiting at a barrier kernel."""
+    pc, why = None, ""
+    try:
+        pc = D.PeerCollator(rank, world, dev, per, N, dtype=dtype)
+    except RuntimeError as e:
+        why = str(e)
+    ok = torch.tensor([1.0 if pc is not None else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() < 1.0:
+        if pc is not None:
+            pc.close()
+        return None, why or "a peer rank could not map this rank's buffers"
+    return pc, ""
+
+
 def run_backsolve(torch, kkt, dev, stream, flush, peaks):
     """stand-alone KKT backsolve: factor once, then time backsolves (inputs >> L2)"""
     Bk = 16384
@@ -581,10 +596,7 @@ def run_config4(args, torch, dist, D, S, W, _lib, dev, rank, world, col, max_ove
     st = torch.cuda.current_stream(dev)
     pc, method = None, "none (one GPU)"
     if world > 1:
-        try:
-            pc = D.PeerCollator(rank, world, dev, per, N, dtype=np.float32)
-        except RuntimeError:
-            pc = None
+        pc, _ = make_peer_collator(D, dist, torch, rank, world, dev, per, N, np.float32)
     if pc is not None:
         z_all, ii_all = pc.z_all, pc.info_all
         run = lambda: pc.solve_sharded(db, o)

@@ -167,16 +167,27 @@ class PeerCollator:
         self.peers = vp()
         zbytes = world * per * N * 17 * self.np_dtype.itemsize
         with torch.cuda.device(self.device):
-            _check(lib.nmpc_peers_create(world, rank, zbytes, world * per * 4, ctypes.byref(self.peers)))
+            err = None
+            mine = ctypes.create_string_buffer(64)
+            if lib.nmpc_peers_create(world, rank, zbytes, world * per * 4, ctypes.byref(self.peers)) != 0 or \
+                    (world > 1 and lib.nmpc_peers_export(self.peers, mine) != 0):
+                err = _lib.last_error()
             if world > 1:
                 if handles is None:
+                    # every rank takes part in the exchange, also one whose allocation failed (it sends None): nobody is
+                    # left waiting in the collective
                     import torch.distributed as dist
-                    mine = ctypes.create_string_buffer(64)
-                    _check(lib.nmpc_peers_export(self.peers, mine))
                     box = [None] * world
-                    dist.all_gather_object(box, mine.raw, group=group)
-                    handles = b"".join(box)
-                _check(lib.nmpc_peers_connect(self.peers, handles))
+                    dist.all_gather_object(box, None if err else mine.raw, group=group)
+                    if any(h is None for h in box):
+                        err = err or "a peer rank could not allocate or export its buffers"
+                    else:
+                        handles = b"".join(box)
+                if err is None:
+                    _check(lib.nmpc_peers_connect(self.peers, handles))
+            if err is not None:
+                self.close()
+                raise RuntimeError(f"nmpc_peers setup failed: {err}")
         t_dt = torch.float64 if self.np_dtype == np.float64 else torch.float32
         self.z_all = _wrap_device_memory(torch, lib.nmpc_peers_z(self.peers), (world * per, N, 17), t_dt, self.device, self)
         self.info_all = _wrap_device_memory(torch, lib.nmpc_peers_info(self.peers), (world * per, 4), torch.int32, self.device, self)
