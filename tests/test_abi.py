@@ -180,3 +180,33 @@ def test_argument_checks_of_the_kernels_around_the_solve(cuda_lib):
     sv = cuda_lib.nmpc_solve_batch_f64
     assert sv(2, 20, 6, vp(8), vp(16), vp(32), vp(40), vp(64), 0, ctypes.byref(o), vp(96), vp(128), vp(160), None) < 0
     assert b"16-byte" in cuda_lib.nmpc_last_error()
+
+
+def test_argument_checks_of_the_multi_gpu_entry_points(cuda_lib):
+    """nmpc_peers_* / nmpc_solve_batch_sharded_* reject bad arguments before any CUDA or NCCL call (runs without a GPU)."""
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    mk = cuda_lib.nmpc_peers_create
+    mk.restype = i
+    mk.argtypes = [i, i, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(vp)]
+    out = vp()
+    assert mk(0, 0, 1024, 16, ctypes.byref(out)) == -11            # world < 1
+    assert mk(17, 0, 1024, 16, ctypes.byref(out)) == -11           # more ranks than a node's peer table holds
+    assert mk(2, 2, 1024, 16, ctypes.byref(out)) == -11            # rank out of range
+    assert mk(2, 0, 0, 16, ctypes.byref(out)) == -11               # empty buffer
+    assert b"world=" in cuda_lib.nmpc_last_error() and not out.value
+    for name, n_extra in (("nmpc_solve_batch_sharded_p2p_f64", 2), ("nmpc_solve_batch_sharded_p2p_f32", 1)):
+        f = getattr(cuda_lib, name)
+        f.restype = i
+        f.argtypes = [vp, i, i, i] + [vp] * 5 + [i, vp, vp] + ([i, vp] if n_extra == 2 else [vp])
+        assert f(None, 4, 20, 8, None, None, None, None, None, 0, None, None, *([0, None] if n_extra == 2 else [None])) == -11
+    for name in ("nmpc_peers_barrier", "nmpc_peers_status", "nmpc_peers_export", "nmpc_peers_connect"):
+        f = getattr(cuda_lib, name)
+        f.restype = i
+        f.argtypes = [vp, vp] if name != "nmpc_peers_status" else [vp]
+        assert f(*([None] * len(f.argtypes))) == -11
+    cuda_lib.nmpc_peers_destroy.argtypes = [vp]
+    assert cuda_lib.nmpc_peers_destroy(None) == 0
+    sh = cuda_lib.nmpc_solve_batch_sharded_f64
+    sh.restype = i
+    sh.argtypes = [vp, i, i, i] + [vp] * 5 + [i, vp, vp, vp, vp, i, vp]
+    assert sh(None, 4, 20, 8, None, None, None, None, None, 0, None, None, None, None, 0, None) < 0
