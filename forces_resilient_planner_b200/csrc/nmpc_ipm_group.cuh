@@ -16,8 +16,10 @@
 //     -- described by per-thread offset tables built once, so all threads run ONE instruction stream (no divergent
 //     formula branches); five CTA barriers per stage replace the ~110-instruction serial chains of the one-warp sweep,
 //     and the back-substitution that only the rollout needs (the gains) runs on warp 0 beside the rank-4 update;
-//   * model evaluation (one stage per thread: a serial chain per stage, it does not get shorter), forward rollout and
-//     costates (short dependent chains over the stages) stay on warp 0 and reuse the one-warp code.
+//   * model evaluation: one stage per lane, the stage's work dealt to four warps by kind (dynamics + Jacobian + J'y |
+//     objective | bound barriers | corridor rows), the stationarity residual assembled by all threads afterwards;
+//   * forward rollout as a closed-loop recursion (transition matrices built by all threads, 13 multiply-adds per stage on
+//     warp 0), costates from the stored cost-to-go in one parallel step.
 //
 // No register parking and no overlay: with few resident problems shared memory is not what limits anything.
 #pragma once
@@ -40,7 +42,10 @@ template <int N> struct GLayout {
     static constexpr int HDR = Y + N * NXI;
     static constexpr int BND = HDR + N * HDR_S;
     static constexpr int RED = BND + 2 * NZ;            // CTA-reduction scratch: 8 warps x 8 values
-    static constexpr int R_FIXED = RED + 64;
+    static constexpr int JTY = RED + 64;                // evaluate(): J'y per (stage, variable), written by the dynamics warp
+    static constexpr int GP = JTY + N * NZ;             //             cost gradient - E'y - z_l + z_u, written by the objective warp
+    static constexpr int AL = GP + N * NZ;              //             A'lambda per stage (3), written by the corridor-row warp
+    static constexpr int R_FIXED = AL + N * 3 + (N & 1);
     __host__ __device__ static constexpr int s_stride(int mcap) { return mcap | 1; }
     __host__ __device__ static constexpr int s_off(int) { return R_FIXED; }
     __host__ __device__ static constexpr int lc_off(int mcap) { return R_FIXED + N * s_stride(mcap); }
@@ -143,69 +148,97 @@ template <int N> struct GroupSolver {
         }
     }
 
-    // ---------------------------------------------------------------- model evaluation (threads 0 .. N-1) ---
+    // ---------------------------------------------------------------- model evaluation, four warps ---
+    // One stage per lane as in the one-warp kernels, but the stage's work is dealt to four warps by kind, so that the
+    // longest instruction stream -- the Heun step with its Jacobian and J'y -- no longer carries the rest behind it:
+    //   warp 0  dynamics, Jacobian (kept in registers for J'y in double precision, then rounded into the Newton data),
+    //           defects, J'y                                   -> JTY
+    //   warp 1  objective and its gradient, - E'y - z_l + z_u  -> GP
+    //   warp 2  log-barrier terms of the bounds
+    //   warp 3  corridor rows: A'lambda, their share of theta and of the log-barrier   -> AL
+    // then all threads: stationarity residual r = GP + JTY + A'lambda per (stage, variable), its inf-norm, rounded into G.
     __device__ void evaluate(double a, double& f_out, double& th_out, double& ls_out, double& req_out, double& rs_out)
     {
         double f = 0.0, th = 0.0, ls = 0.0, rq = 0.0, rs = 0.0;
-        for (int k = tid; k < N; k += NT) {
-            double zk[NZ], g[NZ];
+        double* JTY = r64 + GL::JTY;
+        double* GP = r64 + GL::GP;
+        double* AL = r64 + GL::AL;
+        if (warp < 4) {
+            for (int k = lane; k < N; k += 32) {
+                const double* hdr = HDR + k * GL::HDR_S;
+                if (warp == 0) {
+                    if (k < N - 1) {
+                        double zk[NZ], c[NXI], jc[NJC], yn[NXI];
 #pragma unroll
-            for (int i = 0; i < NZ; i++) zk[i] = Z[k * NZ + i] + a * (double)DZ[k * NZ + i];
-            const double* hdr = HDR + k * GL::HDR_S;
-            f += objective<double, true>(zk, hdr, k == 0, final_variant && k == N - 1, g);
-            if (k < N - 1) {
-                double c[NXI], jc[NJC], yn[NXI];
-                dynamics<double, true>(zk, hdr + 3, c, jc);
+                        for (int i = 0; i < NZ; i++) zk[i] = Z[k * NZ + i] + a * (double)DZ[k * NZ + i];
+                        dynamics<double, true>(zk, hdr + 3, c, jc);
 #pragma unroll
-                for (int i = 0; i < NXI; i++) {
-                    const int zi = (k + 1) * NZ + e_col(i);
-                    const double d = c[i] - (Z[zi] + a * (double)DZ[zi]);
-                    th += fabs(d);
-                    rq = fmax(rq, fabs(d));
-                    D[k * NXI + i] = (float)d;
-                    yn[i] = Y[(k + 1) * NXI + i] + a * (double)DY[(k + 1) * NXI + i];
+                        for (int i = 0; i < NXI; i++) {
+                            const int zi = (k + 1) * NZ + e_col(i);
+                            const double d = c[i] - (Z[zi] + a * (double)DZ[zi]);
+                            th += fabs(d);
+                            rq = fmax(rq, fabs(d));
+                            D[k * NXI + i] = (float)d;
+                            yn[i] = Y[(k + 1) * NXI + i] + a * (double)DY[(k + 1) * NXI + i];
+                        }
+#pragma unroll
+                        for (int e = 0; e < NJC; e++) JC[k * NJC + e] = (float)jc[e];
+#pragma unroll
+                        for (int i = 0; i < NZ; i++) JTY[k * NZ + i] = jt_y<double>(jc, yn, i);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NZ; i++) JTY[k * NZ + i] = 0.0;
+                    }
+                } else if (warp == 1) {
+                    double zk[NZ], g[NZ];
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) zk[i] = Z[k * NZ + i] + a * (double)DZ[k * NZ + i];
+                    f += objective<double, true>(zk, hdr, k == 0, final_variant && k == N - 1, g);
+                    if (k > 0) {
+#pragma unroll
+                        for (int i = 0; i < NXI; i++) g[i < 9 ? 8 + i : i - 5] -= Y[k * NXI + i] + a * (double)DY[k * NXI + i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) GP[k * NZ + i] = g[i] - ZL[k * NZ + i] + ZU[k * NZ + i];
+                } else if (warp == 2) {
+                    double prod = 1.0;
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) {
+                        const double zi = Z[k * NZ + i] + a * (double)DZ[k * NZ + i];
+                        double sl = zi - lower_bound<double>(i), su = upper_bound<double>(i) - zi;
+                        if (i >= 8 && k == 0) { sl = 1.0; su = 1.0; }
+                        prod *= sl * su;
+                        if (i % 9 == 8 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
+                    }
+                } else {
+                    const int m = live(k);
+                    double al0 = 0.0, al1 = 0.0, al2 = 0.0, prod = 1.0;
+                    for (int j = 0; j < m; j++) {
+                        double r[4]; load_row(k, j, r);
+                        double sj = S[k * SS + j];
+                        const double lj = LC[k * SS + j];
+                        al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
+                        double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
+                        const double adz = r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10];
+                        sj += a * (-rc - adz);
+                        rc *= (1.0 - a);
+                        th += fabs(rc);
+                        prod *= sj;
+                        if ((j & 7) == 7) { ls += log(prod); prod = 1.0; }
+                    }
+                    ls += log(prod);
+                    AL[k * 3] = al0; AL[k * 3 + 1] = al1; AL[k * 3 + 2] = al2;
                 }
-#pragma unroll
-                for (int e = 0; e < NJC; e++) JC[k * NJC + e] = (float)jc[e];
-#pragma unroll
-                for (int i = 0; i < NZ; i++) g[i] += jt_y<double>(jc, yn, i);
             }
-            if (k > 0) {
-#pragma unroll
-                for (int i = 0; i < NXI; i++) g[i < 9 ? 8 + i : i - 5] -= Y[k * NXI + i] + a * (double)DY[k * NXI + i];
-            }
-            double prod = 1.0;
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                double sl = zk[i] - lower_bound<double>(i), su = upper_bound<double>(i) - zk[i];
-                if (i >= 8 && k == 0) { sl = 1.0; su = 1.0; }
-                prod *= sl * su;
-                if (i % 9 == 8 || i == NZ - 1) { ls += log(prod); prod = 1.0; }
-            }
-            const int m = live(k);
-            double al0 = 0.0, al1 = 0.0, al2 = 0.0;
-            for (int j = 0; j < m; j++) {
-                double r[4]; load_row(k, j, r);
-                double sj = S[k * SS + j];
-                const double lj = LC[k * SS + j];
-                al0 += r[0] * lj; al1 += r[1] * lj; al2 += r[2] * lj;
-                double rc = r[0] * Z[k * NZ + 8] + r[1] * Z[k * NZ + 9] + r[2] * Z[k * NZ + 10] - (r[3] + C::hu) + sj;
-                const double adz = r[0] * (double)DZ[k * NZ + 8] + r[1] * (double)DZ[k * NZ + 9] + r[2] * (double)DZ[k * NZ + 10];
-                sj += a * (-rc - adz);
-                rc *= (1.0 - a);
-                th += fabs(rc);
-                prod *= sj;
-                if ((j & 7) == 7) { ls += log(prod); prod = 1.0; }
-            }
-            ls += log(prod);
-            g[8] += al0; g[9] += al1; g[10] += al2;
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                double r = g[i] - ZL[k * NZ + i] + ZU[k * NZ + i];
-                if (i >= 8 && k == 0) r = 0.0;
-                rs = fmax(rs, fabs(r));
-                G[k * NZ + i] = (float)r;
-            }
+        }
+        __syncthreads();
+        for (int e = tid; e < N * NZ; e += NT) {
+            const int k = e / NZ, i = e - k * NZ;
+            double r = GP[e] + JTY[e];
+            if (i >= 8 && i < 11) r += AL[k * 3 + i - 8];
+            if (i >= 8 && k == 0) r = 0.0;
+            rs = fmax(rs, fabs(r));
+            G[e] = (float)r;
         }
         double v[5] = {f, th, ls, rq, rs};
         const int ops[5] = {0, 0, 0, 1, 1};
