@@ -216,7 +216,7 @@ int solve_mixed(int B, int N, int mcap, const void* xinit, const void* z0, const
     if (peers) prm.peers = *peers;
     std::memcpy(&prm.o, &o, sizeof(o));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // group: the low-latency variant, one warp-group (128 threads) per problem (nmpc_ipm_group.cuh)
+    // group: the low-latency variant, one warp-group (256 threads) per problem (nmpc_ipm_group.cuh)
     if (int rc = group ? (N == 20 ? launch_group<20>(prm, st) : launch_group<40>(prm, st))
                        : (N == 20 ? launch_mixed<20>(prm, st) : launch_mixed<40>(prm, st))) return rc;
     if (o.mixed < 0) return 0;                      // opts.mixed = -1: no fp64 safety net (tests, profiling)
