@@ -241,6 +241,10 @@ def test_cpp_dropin_demo_runs_the_planner_call_sequence():
     out = subprocess.run([os.path.join(host, "pipeline_demo")], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("64/64 accepted") == 3 and out.stdout.count("corridor overflow 0") == 3, out.stdout
+    # host/sharded_demo.cpp: the multi-GPU host side from C++ -- one process per rank, CUDA IPC handle exchange, the fused
+    # peer-store collation; every rank re-solves every shard and compares bit for bit (ranks share the GPU if there is one)
+    out = subprocess.run([os.path.join(host, "sharded_demo"), "2", "32"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "0 of 2 slices differ" in out.stdout and "64 / 64 with exit flag 1" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.parametrize("maker,kw,mixed", [(W.config2, dict(B=4096), False), (W.config3, dict(B=4096), False),
