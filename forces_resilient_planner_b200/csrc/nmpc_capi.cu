@@ -919,6 +919,7 @@ int nmpc_peers_export(nmpc_peers* p, unsigned char handle[64])
 int nmpc_peers_connect(nmpc_peers* p, const unsigned char* handles)
 {
     if (!p || !handles) return fail(NMPC_ERR_ARG, "null pointer argument");
+    if (p->world == 1) return 0;                                  // nothing to map
     if (p->connected) return fail(NMPC_ERR_ARG, "already connected");
     for (int r = 0; r < p->world; r++) {
         if (r == p->rank) continue;

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <vector>
 
+#include <csignal>
 #include <sys/socket.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -140,6 +141,7 @@ int main(int argc, char** argv)
 {
     const int world = argc > 1 ? std::atoi(argv[1]) : 2, B = argc > 2 ? std::atoi(argv[2]) : 64;
     if (world < 1 || world > 16 || B < 2 || (B & 1)) { std::printf("usage: sharded_demo [world 1..16] [even problems per rank]\n"); return 2; }
+    std::signal(SIGPIPE, SIG_IGN);                                // a rank that died shows up as a failed write, not as a signal
     std::vector<int> fds(world);
     std::vector<pid_t> pids(world);
     for (int r = 0; r < world; r++) {                             // fork BEFORE any CUDA call: a CUDA context does not survive fork()

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3])
 def test_peer_store_collation_matches_local_solves(world):
     port = _free_port()
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "tools", "p2p_worker.py"), str(r), str(world), str(port)],
