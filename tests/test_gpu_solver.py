@@ -250,15 +250,18 @@ def test_cpp_dropin_demo_runs_the_planner_call_sequence():
 @pytest.mark.parametrize("maker,kw,mixed", [(W.config2, dict(B=4096), False), (W.config3, dict(B=4096), False),
                                             (W.config2, dict(B=1024, variant=1), False),
                                             (W.config2, dict(B=4096), True), (W.config3, dict(B=4096), True),
-                                            (W.config2, dict(B=1024, variant=1), True)])
+                                            (W.config2, dict(B=1024, variant=1), True),
+                                            (W.config2, dict(B=4096), "group"), (W.config3, dict(B=4096), "group"),
+                                            (W.config2, dict(B=1024, variant=1), "group")])
 def test_whole_batch_passes_forcespro_acceptance_with_reference_callbacks(maker, kw, mixed):
     """Tier bar #1 at BASELINE size: EVERY problem of config 2 (4096), config 3 (4096 of its 65536) and the final
-    variant (1024) -- through the fp64 kernel and through the mixed-precision kernel -- is re-evaluated with the
+    variant (1024) -- through the fp64 kernel, the mixed-precision kernel and the warp-group kernel (the one the
+    reference symbols run on) -- is re-evaluated with the
     reference's own casadi2forces callbacks (oracle/_ref; oracle/kkt_check.c) at the returned point and multipliers:
     the four inf-norms ForcesPro stops on are <= 1e-4, every multiplier is non-negative (a sign-blind complementarity
     check would let a negative one through), and the residuals the kernel reports are the ones recomputed here."""
     b = maker(**kw)
-    res, mult = S.solve_with_multipliers(b, mixed=mixed)
+    res, mult = S.solve_with_multipliers(b, mixed=bool(mixed), lowlatency=(mixed == "group"))
     assert np.all(res.flag == 1)
     chk, used_ref = H.kkt_residuals_batch(b, res.z, mult["y"], mult["zl"], mult["zu"], mult["lc"], variant=b.variant)
     assert used_ref == ref_model.available()
@@ -320,13 +323,13 @@ def test_infeasible_initial_state_is_reported_not_solved():
 
 def test_kkt_points_match_independent_slsqp_solutions():
     """SURVEY.md 7-1d / 8c pin 3 on the device: 100 instances solved by scipy SLSQP driving the reference's callbacks
-    (tests/golden/slsqp_kkt_points.npz, made by tests/golden/make_slsqp_golden.py) against the fp64 kernel and the
-    mixed-precision kernel.  Every instance is reported; see test_oracle_solver.py for the same check of the CPU port."""
+    (tests/golden/slsqp_kkt_points.npz, made by tests/golden/make_slsqp_golden.py) against the fp64 kernel, the
+    mixed-precision kernel and the warp-group kernel.  Every instance is reported; see test_oracle_solver.py for the same check of the CPU port."""
     g = np.load(os.path.join(GOLD_DIR, "slsqp_kkt_points.npz"))
     for name, maker in (("config2", lambda: W.config2(60)), ("config3", lambda: W.config3(40))):
         sel = g["workload"] == name
         b = maker()
-        for r in (S.solve_host(b), S.solve_host(b, mixed=True)):
+        for r in (S.solve_host(b), S.solve_host(b, mixed=True), S.solve(b, lowlatency=True)):
             rep = H.compare_with_slsqp(b, r.z, r.flag, g["index"][sel], g["z"][sel], g["fun"][sel])
             assert rep["n"] == int(sel.sum()) and rep["n_same_point"] >= rep["n"] - rep["n_slsqp_worse"], rep
             assert rep["n_ours_worse"] == 0, rep
@@ -361,7 +364,7 @@ def test_mixed_precision_meets_the_reference_tolerances(maker, kw):
 
 @pytest.mark.parametrize("maker,kw", [(W.config2, dict(B=300)), (W.config3, dict(B=300)), (W.config2, dict(B=64, variant=1)),
                                       (W.config4, dict(side=12, n_stages=40)), (W.config1, dict())])
-def test_warp_group_kernel_is_the_mixed_kernel_spread_over_128_threads(maker, kw):
+def test_warp_group_kernel_is_the_mixed_kernel_spread_over_256_threads(maker, kw):
     """nmpc_solve_batch_lowlatency_f64 (one warp-group per problem) against the one-warp mixed-precision kernel and the fp64
     CPU port: same exit flags, same KKT points (both stop inside the 1e-4 residual ball: |dz| <= 1e-3 vs fp64), iteration
     counts equal to the one-warp kernel's on >= 97 % of the problems (the two sweeps round differently), and every point
