@@ -292,10 +292,10 @@ struct Arena {
         return 0;
     }
 };
-constexpr int kHostStreams = 3;
+constexpr int kHostStreams = 16;
 struct HostCtx {
     Arena arena;
-    cudaStream_t streams[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kHostStreams] = {};
 };
 std::mutex g_host_mutex;   // the reference solver is non-reentrant (static workspace); mirror that
 HostCtx g_host[kMaxDevices];
@@ -336,6 +336,25 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     // per-problem block keeps the 16-byte alignment the TMA copies need (fp32 and fp64).
     const int n_chunks = B >= 4096 ? 8 : (B >= 2048 ? 4 : 1);
     const int per = ((B + n_chunks - 1) / n_chunks + 3) & ~3;
+    // Pinned (device-accessible) result buffers are written by the kernel itself: the epilogue of every solve stores its
+    // solution to the device copy AND straight into the caller's buffer (one more destination of store_solution, as for
+    // the multi-GPU peers), so the 2.7 KB per problem cross PCIe while the rest of the batch is still being solved.
+    // Otherwise the kernels of all chunks end together and their device-to-host copies queue up behind the last one.
+    char* hz_direct = nullptr;
+    int* hii_direct = nullptr;
+    {
+        const char* off = std::getenv("NMPC_B200_DIRECT_HOST");
+        cudaPointerAttributes pa;
+        if (!(off && off[0] == '0')) {
+            if (cudaPointerGetAttributes(&pa, z_out) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+                (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15) == 0)
+                hz_direct = static_cast<char*>(pa.devicePointer);
+            if (hz_direct && cudaPointerGetAttributes(&pa, info_int) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+                (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15) == 0)
+                hii_direct = static_cast<int*>(pa.devicePointer);
+        }
+        cudaGetLastError();                                   // a pageable pointer makes the query fail on old drivers: not an error here
+    }
     auto enqueue = [&]() -> int {
         for (int c = 0, lo = 0; lo < B; c++, lo += per) {
             const int nb = (B - lo < per) ? B - lo : per;
@@ -348,18 +367,24 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
             if (pr) CUDA_TRY(cudaMemcpyAsync(base + o_r + lo * pr, hr + lo * pr, nb * pr, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(base + o_n + lo * pn, nrows + (size_t)lo * N, nb * pn, cudaMemcpyHostToDevice, st));
             int* d_ii = reinterpret_cast<int*>(base + o_ii + lo * pii);
+            nmpc::PeerOut po;
+            if (hz_direct) {
+                po.n = 1;
+                po.z[0] = hz_direct + lo * pz;
+                po.info[0] = hii_direct ? hii_direct + (size_t)lo * 4 : nullptr;
+            }
             int rc;
             if (mixed)
                 rc = solve_mixed(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
                                  reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
-                                 base + o_ir + lo * pir, st, esz == 4, nullptr, nullptr, nullptr, nullptr, nullptr, group);
+                                 base + o_ir + lo * pir, st, esz == 4, nullptr, nullptr, nullptr, nullptr, nullptr, group, &po);
             else
                 rc = solve_device(nb, N, mcap, base + o_x + lo * px, base + o_z + lo * pz, base + o_h + lo * ph, base + o_r + lo * pr,
                                   reinterpret_cast<const int*>(base + o_n + lo * pn), variant, opts, base + o_zo + lo * pz, d_ii,
-                                  base + o_ir + lo * pir, st);
+                                  base + o_ir + lo * pir, st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, &po);
             if (rc) return rc;
-            CUDA_TRY(cudaMemcpyAsync(hzo + lo * pz, base + o_zo + lo * pz, nb * pz, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(info_int + (size_t)lo * 4, d_ii, nb * pii, cudaMemcpyDeviceToHost, st));
+            if (!hz_direct) CUDA_TRY(cudaMemcpyAsync(hzo + lo * pz, base + o_zo + lo * pz, nb * pz, cudaMemcpyDeviceToHost, st));
+            if (!hii_direct) CUDA_TRY(cudaMemcpyAsync(info_int + (size_t)lo * 4, d_ii, nb * pii, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(hir + lo * pir, base + o_ir + lo * pir, nb * pir, cudaMemcpyDeviceToHost, st));
         }
         return 0;

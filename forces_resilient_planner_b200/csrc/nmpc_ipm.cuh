@@ -42,12 +42,14 @@ struct Opts {
 // Multi-GPU collation by peer stores (nmpc_peers_* of the C ABI): base pointers of THIS rank's slice inside every other
 // rank's copy of the collation buffers, mapped into this process by CUDA IPC.  The epilogue of a solve writes the
 // solution and the four info integers to its own buffers and to all of these, so the exchange rides along with the
-// compute (NVLink stores spread over the whole kernel) and nothing is left to gather afterwards but a barrier.
+// compute (NVLink stores spread over the whole kernel) and nothing is left to gather afterwards but a barrier.  The
+// host-pointer entry points use the same mechanism with ONE extra destination: the caller's pinned result buffer, so the
+// solutions cross PCIe while the batch is still being solved instead of in a copy after the last kernel.
 constexpr int MAX_PEERS = 15;
 struct PeerOut {
     int n = 0;
     void* z[MAX_PEERS];
-    int* info[MAX_PEERS];
+    int* info[MAX_PEERS];      // may be null: solution only
 };
 
 // Problem data and results are arrays of T in HBM, or -- io32, fp64 kernel only: the re-solve of the
@@ -235,7 +237,8 @@ __device__ __forceinline__ void store_solution(const PeerOut& po, void* z_out, i
     if (tid == 0) {
         int* ii = info_int + b * 4;
         ii[0] = flag; ii[1] = it; ii[2] = nbt; ii[3] = resolved;
-        for (int p = 0; p < po.n; p++) *reinterpret_cast<int4*>(po.info[p] + b * 4) = make_int4(flag, it, nbt, resolved);
+        for (int p = 0; p < po.n; p++)
+            if (po.info[p]) *reinterpret_cast<int4*>(po.info[p] + b * 4) = make_int4(flag, it, nbt, resolved);
     }
 }
 
