@@ -145,7 +145,11 @@ int nmpc_solve_batch_ordered_f64(int B, int N, int mcap, const double *xinit, co
                                  int variant, const nmpc_opts *opts, double *z_out, int *info_int,
                                  double *info_real, const int *order, void *cuda_stream);
 
-/* ---- host-pointer API: H2D copies, solve, D2H copies, synchronous --------------------------- */
+/* ---- host-pointer API: H2D copies, solve, D2H copies, synchronous ---------------------------
+ * Large batches are cut into chunks, one stream each, so that copies and kernels overlap.  Any host memory works;
+ * pinned memory (cudaHostAlloc / cudaHostRegister) is faster, and when z_out (and info_int) are pinned and 16-byte
+ * aligned the solve kernel stores each solution straight into them as the problem finishes (no copy after the last
+ * kernel).  $NMPC_B200_DIRECT_HOST=0 turns that off.                                                          */
 int nmpc_solve_batch_host_f64(int B, int N, int mcap, const double *xinit, const double *z0,
                               const double *hdr, const double *rows, const int *nrows, int variant,
                               const nmpc_opts *opts, double *z_out, int *info_int, double *info_real);
