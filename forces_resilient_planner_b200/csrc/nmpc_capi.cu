@@ -292,7 +292,7 @@ struct Arena {
         return 0;
     }
 };
-constexpr int kHostStreams = 16;
+constexpr int kHostStreams = 8;
 struct HostCtx {
     Arena arena;
     cudaStream_t streams[kHostStreams] = {};
@@ -316,7 +316,8 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return fail(NMPC_ERR_CUDA, "device ordinal %d out of range", dev);
     HostCtx& ctx = g_host[dev];
-    for (int i = 0; i < kHostStreams; i++)
+    const int n_chunks = B >= 4096 ? 8 : (B >= 2048 ? 4 : 1);     // one stream per chunk (kHostStreams >= 8)
+    for (int i = 0; i < n_chunks; i++)
         if (!ctx.streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx.streams[i], cudaStreamNonBlocking));
     const size_t n_x = (size_t)B * 9 * esz, n_z = (size_t)B * N * 17 * esz;
     const size_t n_h = (size_t)B * N * 10 * esz, n_r = (size_t)B * N * mcap * 4 * esz;
@@ -334,7 +335,6 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     // i+1 and the D2H copy of chunk i-1 overlap the solve of chunk i, and the next chunk's CTAs fill
     // the tail wave of the previous kernel.  Chunk boundaries are multiples of 4 problems, so every
     // per-problem block keeps the 16-byte alignment the TMA copies need (fp32 and fp64).
-    const int n_chunks = B >= 4096 ? 8 : (B >= 2048 ? 4 : 1);
     const int per = ((B + n_chunks - 1) / n_chunks + 3) & ~3;
     // Pinned (device-accessible) result buffers are written by the kernel itself: the epilogue of every solve stores its
     // solution to the device copy AND straight into the caller's buffer (one more destination of store_solution, as for
@@ -392,7 +392,7 @@ int solve_host(int B, int N, int mcap, const void* xinit, const void* z0, const 
     const int rc = enqueue();
     // also on failure: nothing may still be in flight into the shared arena (or the caller's buffers) when we return
     cudaError_t serr = cudaSuccess;
-    for (int i = 0; i < kHostStreams; i++) {
+    for (int i = 0; i < n_chunks; i++) {
         const cudaError_t e = cudaStreamSynchronize(ctx.streams[i]);
         if (e != cudaSuccess && serr == cudaSuccess) serr = e;
     }
