@@ -115,6 +115,22 @@ int launch_group(const nmpc::MixedParams& prm, cudaStream_t st)
 {
     const size_t smem = nmpc::GLayout<N>::bytes(prm.mcap);
     static thread_local size_t configured[kMaxDevices] = {};
+    // more problems than SMs: the variant compiled for two resident CTAs per SM (128 registers per thread) keeps them all
+    // in one wave up to twice the SM count
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    static thread_local int sm_count[kMaxDevices] = {};
+    if (dev >= 0 && dev < kMaxDevices) {
+        if (!sm_count[dev]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        sms = sm_count[dev];
+    }
+    if (N == 20 && prm.B > sms && 2 * smem + 2048 <= 233472) {
+        static thread_local size_t configured2[kMaxDevices] = {};
+        if (int rc = ensure_smem(nmpc::nmpc_ipm_group_kernel<N, 2>, smem, configured2)) return rc;
+        nmpc::nmpc_ipm_group_kernel<N, 2><<<prm.B, nmpc::GROUP_THREADS, smem, st>>>(prm);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (int rc = ensure_smem(nmpc::nmpc_ipm_group_kernel<N>, smem, configured)) return rc;
     nmpc::nmpc_ipm_group_kernel<N><<<prm.B, nmpc::GROUP_THREADS, smem, st>>>(prm);
     CUDA_TRY(cudaGetLastError());

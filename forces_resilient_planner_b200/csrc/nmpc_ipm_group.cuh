@@ -22,6 +22,9 @@
 //     warp 0), costates from the stored cost-to-go in one parallel step.
 //
 // No register parking and no overlay: with few resident problems shared memory is not what limits anything.
+// Two builds: MINB = 1 (255 registers, one CTA per SM) for fleets of at most one problem per SM, MINB = 2 (128 registers,
+// some spills in the model evaluation) so that up to two problems per SM still run as ONE wave (296 problems: 0.53 ms
+// instead of 0.83 ms in two waves, 0.79 ms for the one-warp kernel).
 #pragma once
 #include "nmpc_ipm_mixed.cuh"
 
@@ -682,8 +685,8 @@ template <int N> struct GroupSolver {
 // =====================================================================================
 // the kernel: grid = B CTAs of 256 threads; dynamic smem = GLayout::bytes(mcap)
 // =====================================================================================
-template <int N>
-__global__ void __launch_bounds__(GROUP_THREADS) nmpc_ipm_group_kernel(const MixedParams prm)
+template <int N, int MINB = 1>
+__global__ void __launch_bounds__(GROUP_THREADS, MINB) nmpc_ipm_group_kernel(const MixedParams prm)
 {
     using GL = GLayout<N>;
     using C = Const<double>;

@@ -88,10 +88,12 @@ class RecedingHorizonStream:
         # wave, and every iteration is shorter); its fp64 re-solve of an agent it gives up on rides on the same stream
         self.mixed = mixed
         # the warp-group kernel (nmpc_solve_batch_lowlatency_f64: 256 threads per agent, one agent per SM, ~0.65x the time
-        # per iteration) pays when the fleet leaves most of the GPU idle; default: on for mixed streams of at most one
-        # agent per SM (a second wave would cost more than the shorter iterations save)
+        # per iteration) pays when the fleet leaves most of the GPU idle; default: on for mixed streams of at most two
+        # agents per SM (N = 20: beyond one agent per SM the library switches to its 128-register build, two CTAs per
+        # SM; a second WAVE would cost more than the shorter iterations save)
         if lowlatency is None:
-            lowlatency = mixed and self.B <= torch.cuda.get_device_properties(self.dev).multi_processor_count
+            sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            lowlatency = mixed and self.B <= (2 * sms if self.N == 20 else sms)
         self.lowlatency = bool(lowlatency)
         self.order = torch.arange(self.B, dtype=torch.int32, device=self.dev)
         self.cycle = 0

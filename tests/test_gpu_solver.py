@@ -504,10 +504,11 @@ def test_rank_longest_first_equals_stable_argsort():
         assert np.array_equal(got, want), B
 
 
-@pytest.mark.parametrize("B,expect_group", [(40, True), (200, False)])
+@pytest.mark.parametrize("B,expect_group", [(40, True), (200, True), (400, False)])
 def test_mixed_precision_stream_follows_the_fp64_closed_loop(B, expect_group):
-    """The receding-horizon stream through the mixed-precision kernels (warp-group kernel for a small fleet, one-warp
-    kernel for a large one) against the same stream through the fp64 kernel: every replan converges, the commands agree
+    """The receding-horizon stream through the mixed-precision kernels (warp-group kernel for a small fleet -- its
+    one-CTA-per-SM build at 40 agents, its two-CTAs-per-SM build at 200 --, one-warp kernel for a large one) against the
+    same stream through the fp64 kernel: every replan converges, the commands agree
     to the solver tolerance, the iteration counts agree on >= 95 % of the (agent, replan) pairs."""
     from forces_resilient_planner_b200 import stream as ST
     b = W.config2(B)
